@@ -1,0 +1,114 @@
+/*
+ * liteattn_b200.h -- C ABI of the B200 (sm_100a) QK-Skip attention forward.
+ *
+ * This is the drop-in boundary for the ONE hot path of moonmath-ai/LiteAttention:
+ * the skip-list-gated attention forward + skip-list update that the reference reaches through
+ *     torch.ops.lite_attention.fwd            (hopper/_internal/cpp/flash_api.cpp:1722-1763 schema,
+ *                                              :667-1249 mha_fwd, :915-963 skip-arg plumbing)
+ * Every entry point takes plain pointers/sizes (device pointers unless stated otherwise) and a
+ * cudaStream_t passed as void*.  No torch types.  All functions return 0 on success, a negative
+ * LA_ERR_* code otherwise; la_last_error() returns a thread-local human-readable message.
+ * Nothing here synchronises the host with the device (the reference does not either,
+ * flash_api.cpp:1219-1220).
+ */
+#ifndef LITEATTN_B200_H_
+#define LITEATTN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LA_OK 0
+#define LA_ERR_INVALID (-1)     /* bad argument (shape / stride / alignment / null pointer)          */
+#define LA_ERR_UNSUPPORTED (-2) /* valid for the reference but not built here (e.g. head_dim != 128) */
+#define LA_ERR_CUDA (-3)        /* CUDA driver / runtime error, see la_last_error()                  */
+
+#define LA_ABI_VERSION 1
+
+/* Tile geometry of the skip list.  API-visible: mirrors tile_size_fwd_sm90
+ * (hopper/_internal/cpp/tile_size.h:10-62) == LiteAttention.get_MN (hopper/lite_attention.py:87-111).
+ * bf16, d=128, non-causal -> (128, 176). */
+#define LA_BLOCK_M 128
+#define LA_BLOCK_N 176
+#define LA_HEAD_DIM 128
+
+/* Replaces the used fields of Flash_fwd_params / Qkv_params (hopper/_internal/cpp/flash.h:22-44,
+ * :48-83) and QKSkipMaskArgs (flash.h:12-18, :181-184).  Strides are in ELEMENTS, as in the
+ * reference (set_params_fprop, flash_api.cpp:81-103).  q/k/v/out are bf16 with last-dim stride 1. */
+typedef struct la_fwd_params {
+  const void* q;   /* (b, seqlen_q, h,   d) bf16 */
+  const void* k;   /* (b, seqlen_k, h_k, d) bf16 */
+  const void* v;   /* (b, seqlen_k, h_k, d) bf16 */
+  void* out;       /* (b, seqlen_q, h,   d) bf16, written */
+  float* lse;      /* (b, h, seqlen_q) fp32 contiguous, written; may be NULL */
+  int64_t q_batch_stride, q_row_stride, q_head_stride;
+  int64_t k_batch_stride, k_row_stride, k_head_stride;
+  int64_t v_batch_stride, v_row_stride, v_head_stride;
+  int64_t o_batch_stride, o_row_stride, o_head_stride;
+  int32_t b, h, h_k, seqlen_q, seqlen_k, d;
+  float softmax_scale;
+  /* Skip list that gates whole (Q-tile, K-tile) iterations.  int32, contiguous,
+   * [>=b, h, qtiles, ktiles+1], row = [len, s0, e0, s1, e1, ...] with inclusive descending ranges
+   * (SkipListReader, mainloop_fwd_sm90_tma_gmma_ws.hpp:47-115).  NULL => dense (every tile). */
+  const int32_t* read_list;
+  /* Per-tile QK-skip statistic, fp32 contiguous [b, h, qtiles, ktiles]; for every VISITED tile n
+   * (except the first one of a row, which gets +inf) the kernel writes
+   *     max over the 128 rows of ((m_local - m_prev) * softmax_scale * log2(e))
+   * i.e. the left-hand side of the skip predicate (softmax.h:194).  May be NULL. Unvisited entries
+   * are left untouched. */
+  float* tile_stat;
+} la_fwd_params;
+
+/* Replaces SkipListWriter + the record/loop logic that the reference fuses into the forward
+ * (mainloop_fwd_sm90_tma_gmma_ws.hpp:121-192, :1804-1827).  Here it is a separate HBM-bound kernel. */
+typedef struct la_update_params {
+  const int32_t* read_list;    /* [>=b, h, qtiles, ktiles+1] the list the forward just used  */
+  const int32_t* must_do_list; /* same shape (expanded, lite_attention.py:214-242); may be NULL */
+  int32_t* write_list;         /* same shape; rows are rewritten: [len, entries...]            */
+  const float* tile_stat;      /* [b, h, qtiles, ktiles] from la_fwd_sm100                      */
+  int32_t b, h, qtiles, ktiles;
+  float thr;                   /* vote skip iff !(stat > thr)  (softmax.h:194,207)              */
+  int32_t* overflow_count;     /* optional device counter: rows whose new list would not fit   */
+} la_update_params;
+
+/* O_i/LSE_i partial-attention merge (reference analogue: flash_fwd_combine_kernel.h, disabled in the
+ * shipped build; README.md:222-250 asks callers to do this themselves). */
+typedef struct la_combine_params {
+  const void* const* o_parts;    /* HOST array of n_parts device pointers, each (b, s, h, d) bf16 contiguous */
+  const float* const* lse_parts; /* HOST array of n_parts device pointers, each (b, h, s) fp32 contiguous    */
+  int32_t n_parts;
+  void* out;                     /* (b, s, h, d) bf16 contiguous */
+  float* lse;                    /* (b, h, s) fp32, may be NULL  */
+  int32_t b, h, s, d;
+} la_combine_params;
+
+int la_abi_version(void);
+const char* la_last_error(void);
+
+/* (kBlockM, kBlockN) for a head dim / element size.  Same table as get_MN. Returns LA_ERR_UNSUPPORTED
+ * for geometries whose kernel is not built. */
+int la_get_tile_mn(int head_dim, int element_size, int v_colmajor, int* block_m, int* block_n);
+
+/* Skip-list-gated attention forward (tcgen05/TMEM/TMA kernel). */
+int la_fwd_sm100(const la_fwd_params* p, void* stream);
+
+/* Skip-list update from the per-tile statistic. */
+int la_skip_update_sm100(const la_update_params* p, void* stream);
+
+/* Convenience: la_fwd_sm100 followed by la_skip_update_sm100 on the same stream -- the exact
+ * behaviour of one lite_attention::fwd call with (attn_read_list, attn_must_do_list,
+ * attn_write_list, thr).  upd->read_list / tile_stat are taken from fwd when NULL. */
+int la_fwd_skip_sm100(const la_fwd_params* fwd, const la_update_params* upd, void* stream);
+
+/* Merge n partial attention results by their LSE. */
+int la_combine_sm100(const la_combine_params* p, void* stream);
+
+/* Number of kernels launched through this library by the calling process (for bench accounting). */
+uint64_t la_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LITEATTN_B200_H_ */

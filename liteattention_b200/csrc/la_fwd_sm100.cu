@@ -1,0 +1,395 @@
+// la_fwd_sm100.cu -- skip-list-gated attention forward for B200 (sm_100a).
+//
+// What it computes (restating the reference's behaviour, not its code):
+//   for one (batch b, head h, 128-row Q tile m) walk the K tiles named by the read list
+//   (descending inclusive ranges, SkipListReader, hopper/_internal/cpp/mainloop_fwd_sm90_tma_gmma_ws.hpp:47-115)
+//   and run S = Q K^T -> online softmax -> O += P V on exactly those tiles
+//   (mainloop :1612-1663 first tile, :1667-1755 steady state, softmax.h:139-222, :263-296).
+//   Per visited tile it also emits the left-hand side of the QK-skip predicate (softmax.h:194)
+//   reduced over the tile's 128 rows, which la_skip_update.cu turns into the next list.
+//
+// How (B200-first, nothing shared with the Hopper kernel):
+//   * 10 warps: 8 softmax warps (two warpgroups that split the 176 S columns 88/88, one TMEM lane = one
+//     query row per thread), 1 TMA producer warp, 1 tcgen05 issuer warp.
+//   * Q (128x128), K and V tiles (176x128, 2 stages each) are TMA-loaded into 128B-swizzled smem.
+//   * S = Q K^T : tcgen05.mma kind::f16, M=128 N=176 K=16 x8, SS operands, fp32 accumulator in TMEM;
+//     two S buffers so QK^T of tile i+1 runs under the softmax of tile i.
+//   * P (bf16) is written back over S in TMEM and fed to O += P V as the TMEM A operand
+//     (M=128 N=128 K=16 x11, V is the MN-major smem B operand); O lives in TMEM for the whole CTA.
+//   * TMEM map (512 columns allocated): S0 @0, S1 @176, O @352..479.
+//   * O is rescaled in TMEM only when some row max of the warp actually moved (exact, not lazy).
+#include <cuda_bf16.h>
+
+#include "la_kernels.h"
+#include "la_ptx.cuh"
+#include "la_tmem_ptx.cuh"
+
+namespace la {
+
+namespace {
+
+constexpr int kM = 128;        // query rows per CTA
+constexpr int kN = 176;        // key rows per tile (skip-list granularity, tile_size.h:35-40)
+constexpr int kD = 128;        // head dim
+constexpr int kHalfN = kN / 2; // S columns per softmax warpgroup
+constexpr int kSoftmaxThreads = 256;
+constexpr int kProducerWarp = 8;
+constexpr int kMmaWarp = 9;
+
+constexpr uint32_t kQBlockBytes = kM * 128;   // one 64-column (128 B) swizzled block of Q
+constexpr uint32_t kKVBlockBytes = kN * 128;  // one 64-column block of a K or V tile (22528 = 22 * 1024)
+constexpr uint32_t kQBytes = 2 * kQBlockBytes;
+constexpr uint32_t kKVBytes = 2 * kKVBlockBytes;
+
+constexpr uint32_t kOffQ = 0;
+constexpr uint32_t kOffK = kOffQ + kQBytes;
+constexpr uint32_t kOffV = kOffK + 2 * kKVBytes;
+constexpr uint32_t kOffBar = kOffV + 2 * kKVBytes;
+constexpr uint32_t kOffXchg = kOffBar + 256;
+constexpr uint32_t kOffLx = kOffXchg + 2 * kSoftmaxThreads * 4;
+constexpr uint32_t kOffStat = kOffLx + kSoftmaxThreads * 4;
+constexpr uint32_t kOffSeq = kOffStat + kFwdMaxTiles * 4;
+constexpr uint32_t kSmemUsed = kOffSeq + kFwdMaxTiles * 2;
+static_assert(kSmemUsed + 1024 <= 232448, "shared memory budget (227 KB) exceeded");
+static_assert(kFwdSmemBytes == kSmemUsed + 1024, "keep la_kernels.h in sync");
+
+enum Bar : uint32_t {
+  kBarQFull = 0,
+  kBarKFull = 1,   // +stage
+  kBarKEmpty = 3,  // +stage
+  kBarVFull = 5,
+  kBarVEmpty = 7,
+  kBarSFull = 9,   // +buf
+  kBarPFull = 11,  // +buf
+  kBarPvDone = 13,
+  kNumBars = 14
+};
+
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kTmemS = 0;        // S buffers at 0 and 176
+constexpr uint32_t kTmemO = 2 * kN;   // 352
+
+constexpr uint32_t kIdescQK = make_idesc_bf16(kM, kN, /*b_mn_major=*/0);
+constexpr uint32_t kIdescPV = make_idesc_bf16(kM, kD, /*b_mn_major=*/1);
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);  // .x (low 16 bits) = lo
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(kFwdThreads, 1)
+la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+              const __grid_constant__ CUtensorMap tmap_v, const FwdKernelArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzle atoms need 1024-byte alignment.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t smem_base = smem_u32(smem);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_block = blockIdx.x;
+  const int head = blockIdx.y;
+  const int batch = blockIdx.z;
+  const int head_kv = head / args.h_per_kv;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kOffBar + kNumBars * 8);
+  volatile int* num_tiles_smem = reinterpret_cast<volatile int*>(smem + kOffBar + kNumBars * 8 + 4);
+  float* xchg = reinterpret_cast<float*>(smem + kOffXchg);
+  float* lx = reinterpret_cast<float*>(smem + kOffLx);
+  int* stat_s = reinterpret_cast<int*>(smem + kOffStat);
+  uint16_t* seq = reinterpret_cast<uint16_t*>(smem + kOffSeq);
+  auto bar = [&](uint32_t idx) { return smem_base + kOffBar + idx * 8; };
+
+  // ------------------------------------------------------------------ one-time setup
+  if (threadIdx.x == 0) {
+    mbar_init(bar(kBarQFull), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar(kBarKFull + s), 1);
+      mbar_init(bar(kBarKEmpty + s), 1);
+      mbar_init(bar(kBarVFull + s), 1);
+      mbar_init(bar(kBarVEmpty + s), 1);
+      mbar_init(bar(kBarSFull + s), 1);
+      mbar_init(bar(kBarPFull + s), kSoftmaxThreads / 32);  // one arrival per softmax warp
+    }
+    mbar_init(bar(kBarPvDone), 1);
+    fence_mbar_init();
+  }
+  if (warp == kProducerWarp) {
+    // Decode the read-list row into the flat sequence of K tiles this CTA visits.
+    if (lane == 0) {
+      prefetch_tmap(&tmap_q);
+      prefetch_tmap(&tmap_k);
+      prefetch_tmap(&tmap_v);
+    }
+    int count = 0;
+    if (args.read_list != nullptr) {
+      const int32_t* row = args.read_list +
+                           ((int64_t)(batch * args.h + head) * args.qtiles + m_block) * (int64_t)(args.ktiles + 1);
+      int len = row[0];
+      len = min(max(len, 0), args.ktiles) & ~1;
+      for (int r = 0; r < len; r += 2) {
+        int s = row[1 + r], e = row[2 + r];
+        // The reference does not validate list contents (a malformed list is an OOB tile index there);
+        // here out-of-range ranges are clamped so that the kernel can never read outside K/V.
+        s = min(s, args.ktiles - 1);
+        e = max(e, 0);
+        const int nt = s - e + 1;
+        if (nt <= 0) continue;
+        const int room = kFwdMaxTiles - count;
+        const int take = min(nt, room);
+        for (int j = lane; j < take; j += 32) seq[count + j] = (uint16_t)(s - j);
+        count += take;
+      }
+    } else {
+      count = min(args.ktiles, kFwdMaxTiles);
+      for (int j = lane; j < count; j += 32) seq[j] = (uint16_t)(args.ktiles - 1 - j);
+    }
+    const int neg_inf_ord = float_to_ordered(-INFINITY);
+    for (int j = lane; j < count; j += 32) stat_s[j] = (j == 0) ? float_to_ordered(INFINITY) : neg_inf_ord;
+    if (lane == 0) *num_tiles_smem = count;
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const int T = *num_tiles_smem;
+
+  if (warp == kProducerWarp) {
+    // ================================================================ TMA producer (one lane)
+    if (lane == 0 && T > 0) {
+      mbar_arrive_expect_tx(bar(kBarQFull), kQBytes);
+      tma_load_4d(smem_base + kOffQ, &tmap_q, bar(kBarQFull), 0, m_block * kM, head, batch);
+      tma_load_4d(smem_base + kOffQ + kQBlockBytes, &tmap_q, bar(kBarQFull), 64, m_block * kM, head, batch);
+
+      auto load_kv = [&](const CUtensorMap* tm, uint32_t off, uint32_t full0, uint32_t empty0, int i) {
+        const int s = i & 1;
+        const int n = seq[i];
+        mbar_wait(bar(empty0 + s), ((i >> 1) & 1) ^ 1, 1, i);
+        mbar_arrive_expect_tx(bar(full0 + s), kKVBytes);
+        const uint32_t dst = smem_base + off + s * kKVBytes;
+        tma_load_4d(dst, tm, bar(full0 + s), 0, n * kN, head_kv, batch);
+        tma_load_4d(dst + kKVBlockBytes, tm, bar(full0 + s), 64, n * kN, head_kv, batch);
+      };
+      load_kv(&tmap_k, kOffK, kBarKFull, kBarKEmpty, 0);
+      for (int i = 0; i < T; ++i) {
+        if (i + 1 < T) load_kv(&tmap_k, kOffK, kBarKFull, kBarKEmpty, i + 1);
+        load_kv(&tmap_v, kOffV, kBarVFull, kBarVEmpty, i);
+      }
+    }
+    __syncwarp();
+  } else if (warp == kMmaWarp) {
+    // ================================================================ tcgen05 issuer (one lane)
+    if (lane == 0 && T > 0) {
+      const uint64_t q_desc = make_smem_desc_sw128(smem_base + kOffQ, 16, 1024);
+      auto issue_qk = [&](int i) {
+        const int s = i & 1;
+        mbar_wait(bar(kBarKFull + s), (i >> 1) & 1, 2, i);
+        tc_fence_after();
+        const uint64_t k_desc = make_smem_desc_sw128(smem_base + kOffK + s * kKVBytes, 16, 1024);
+        const uint32_t d_tmem = tmem_base + kTmemS + s * kN;
+#pragma unroll
+        for (int j = 0; j < kD / 16; ++j) {
+          // K-major SW128: 4 k-steps of 32 B inside a 128 B swizzle row, then the next 64-column block.
+          const uint32_t a_off = ((j >> 2) * kQBlockBytes + (j & 3) * 32) >> 4;
+          const uint32_t b_off = ((j >> 2) * kKVBlockBytes + (j & 3) * 32) >> 4;
+          umma_ss(d_tmem, q_desc + a_off, k_desc + b_off, kIdescQK, j > 0);
+        }
+        tc_commit(bar(kBarKEmpty + s));  // K stage reusable once these MMAs retire
+        tc_commit(bar(kBarSFull + s));   // S(i) ready for the softmax warps
+      };
+      mbar_wait(bar(kBarQFull), 0, 3, 0);
+      issue_qk(0);
+      for (int i = 0; i < T; ++i) {
+        if (i + 1 < T) issue_qk(i + 1);
+        const int s = i & 1;
+        mbar_wait(bar(kBarVFull + s), (i >> 1) & 1, 4, i);
+        mbar_wait(bar(kBarPFull + s), (i >> 1) & 1, 5, i);
+        tc_fence_after();
+        // V tile is [176 kv rows][64 d] x 2 blocks, i.e. the MN-major B operand:
+        //   LBO = distance between the two 64-wide d blocks, SBO = 8 kv rows (1024 B); one k-step = 16 rows.
+        const uint64_t v_desc = make_smem_desc_sw128(smem_base + kOffV + s * kKVBytes, kKVBlockBytes, 1024);
+        const uint32_t p_tmem = tmem_base + kTmemS + s * kN;
+#pragma unroll
+        for (int j = 0; j < kN / 16; ++j) {
+          umma_ts(tmem_base + kTmemO, p_tmem + j * 8, v_desc + ((j * 16 * 128) >> 4), kIdescPV, (i > 0) || (j > 0));
+        }
+        tc_commit(bar(kBarVEmpty + s));
+        tc_commit(bar(kBarPvDone));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================================================ softmax warps (256 threads)
+    const int wg = warp >> 2;                 // column half: 0 -> S[:, 0:88), 1 -> S[:, 88:176)
+    const int row = (warp & 3) * 32 + lane;   // TMEM lane == query row inside the tile
+    const int tid = threadIdx.x;              // 0..255
+    const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
+    const float c = args.scale_log2;
+    const int q_row = m_block * kM + row;
+
+    float m_run = -INFINITY;  // true running row max (raw S units)
+    float l_run = 0.f;        // this thread's partial row sum (its 88 columns)
+
+    for (int i = 0; i < T; ++i) {
+      const int buf = i & 1;
+      const int n = seq[i];
+      mbar_wait(bar(kBarSFull + buf), (i >> 1) & 1, 6, i);
+      tc_fence_after();
+
+      float s[kHalfN];
+      uint32_t* sr = reinterpret_cast<uint32_t*>(s);
+      const uint32_t s_addr = tmem_base + kTmemS + buf * kN + wg * kHalfN + lane_field;
+      tmem_ld_x32(s_addr, sr);
+      tmem_ld_x32(s_addr + 32, sr + 32);
+      tmem_ld_x16(s_addr + 64, sr + 64);
+      tmem_ld_x8(s_addr + 80, sr + 80);
+      tmem_wait_ld();
+
+      if (i == 0) {
+        // Key columns >= seqlen_k are masked in the FIRST processed tile only (mask.h:66-76, mainloop :1626).
+        const int lim = args.seqlen_k - (n * kN + wg * kHalfN);
+        if (lim < kHalfN) {
+#pragma unroll
+          for (int j = 0; j < kHalfN; ++j)
+            if (j >= lim) s[j] = -INFINITY;
+        }
+        if (args.dbg != nullptr && blockIdx.x == args.dbg_block && blockIdx.y == 0 && blockIdx.z == 0) {
+#pragma unroll
+          for (int j = 0; j < kHalfN; ++j) args.dbg[row * kN + wg * kHalfN + j] = s[j];
+        }
+      }
+
+      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+      for (int j = 4; j < kHalfN; j += 4) {
+        mx0 = fmaxf(mx0, s[j]);
+        mx1 = fmaxf(mx1, s[j + 1]);
+        mx2 = fmaxf(mx2, s[j + 2]);
+        mx3 = fmaxf(mx3, s[j + 3]);
+      }
+      const float m_half = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      // Exchange the half-row maxima between the two warps that own the same 32 rows.
+      xchg[buf * kSoftmaxThreads + tid] = m_half;
+      named_bar_sync(1 + (warp & 3), 64);
+      const float m_loc = fmaxf(m_half, xchg[buf * kSoftmaxThreads + (tid ^ 128)]);
+
+      const float m_prev = m_run;
+      const float m_new = fmaxf(m_prev, m_loc);
+      if (wg == 0 && i > 0) {
+        // QK-skip statistic: (m_local - m_prev) * scale_log2, reduced with max over the tile's rows.
+        const float d = __fmul_rn(__fsub_rn(m_loc, m_prev), c);
+        int od = (d != d) ? float_to_ordered(-INFINITY) : float_to_ordered(d);  // NaN compares false upstream
+        od = __reduce_max_sync(0xffffffffu, od);
+        if (lane == 0) atomicMax(&stat_s[i], od);
+      }
+      const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = ex2_approx((m_prev - m_safe) * c);
+      m_run = m_new;
+      const float neg_mc = -m_safe * c;
+
+      uint32_t pr[kHalfN / 2];
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int j = 0; j < kHalfN; j += 4) {
+        const float p0 = ex2_approx(__fmaf_rn(s[j], c, neg_mc));
+        const float p1 = ex2_approx(__fmaf_rn(s[j + 1], c, neg_mc));
+        const float p2 = ex2_approx(__fmaf_rn(s[j + 2], c, neg_mc));
+        const float p3 = ex2_approx(__fmaf_rn(s[j + 3], c, neg_mc));
+        a0 += p0;
+        a1 += p1;
+        a2 += p2;
+        a3 += p3;
+        pr[j / 2] = pack_bf16(p0, p1);
+        pr[j / 2 + 1] = pack_bf16(p2, p3);
+      }
+      l_run = l_run * alpha + ((a0 + a1) + (a2 + a3));  // row sum uses fp32 P, before bf16 rounding
+
+      if (i > 0) {
+        // O may only be touched between PV(i-1) retiring and PV(i) being issued.
+        mbar_wait(bar(kBarPvDone), (i - 1) & 1, 7, i);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+          const uint32_t o_addr = tmem_base + kTmemO + wg * 64 + lane_field;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float o[32];
+            tmem_ld_x32(o_addr + h * 32, reinterpret_cast<uint32_t*>(o));
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] *= alpha;
+            tmem_st_x32(o_addr + h * 32, reinterpret_cast<uint32_t*>(o));
+          }
+        }
+      }
+      // P (bf16 pairs) goes over the first 88 columns of this S buffer: wg0 -> [0,44), wg1 -> [44,88).
+      // Safe: both half-row owners finished reading S before the named barrier above.
+      const uint32_t p_addr = tmem_base + kTmemS + buf * kN + wg * (kHalfN / 2) + lane_field;
+      tmem_st_x32(p_addr, pr);
+      tmem_st_x8(p_addr + 32, pr + 32);
+      tmem_st_x4(p_addr + 40, pr + 40);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(kBarPFull + buf));
+    }
+
+    // ---------------------------------------------------------------- epilogue
+    float inv = 0.f, lse = -INFINITY;
+    if (T > 0) {
+      lx[tid] = l_run;
+      named_bar_sync(1 + (warp & 3), 64);
+      const float l_tot = l_run + lx[tid ^ 128];
+      const bool bad = (l_tot == 0.f) || (l_tot != l_tot);
+      inv = bad ? 0.f : 1.0f / l_tot;                                              // softmax.h:283-293
+      lse = bad ? -INFINITY : m_run * args.softmax_scale + logf(l_tot);
+      mbar_wait(bar(kBarPvDone), (T - 1) & 1, 8, T);
+      tc_fence_after();
+    }
+    float o[64];
+    if (T > 0) {
+      const uint32_t o_addr = tmem_base + kTmemO + wg * 64 + lane_field;
+      tmem_ld_x32(o_addr, reinterpret_cast<uint32_t*>(o));
+      tmem_ld_x32(o_addr + 32, reinterpret_cast<uint32_t*>(o) + 32);
+      tmem_wait_ld();
+    } else {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) o[j] = 0.f;
+    }
+    if (q_row < args.seqlen_q) {
+      __nv_bfloat16* optr = args.out + (int64_t)batch * args.o_batch_stride + (int64_t)q_row * args.o_row_stride +
+                            (int64_t)head * args.o_head_stride + wg * 64;
+      uint4* dst = reinterpret_cast<uint4*>(optr);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        uint4 v;
+        v.x = pack_bf16(o[8 * j + 0] * inv, o[8 * j + 1] * inv);
+        v.y = pack_bf16(o[8 * j + 2] * inv, o[8 * j + 3] * inv);
+        v.z = pack_bf16(o[8 * j + 4] * inv, o[8 * j + 5] * inv);
+        v.w = pack_bf16(o[8 * j + 6] * inv, o[8 * j + 7] * inv);
+        dst[j] = v;
+      }
+      if (wg == 0 && args.lse != nullptr)
+        args.lse[((int64_t)batch * args.h + head) * args.seqlen_q + q_row] = lse;
+    }
+  }
+
+  // ------------------------------------------------------------------ teardown
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (args.tile_stat != nullptr) {
+    float* stat_row = args.tile_stat + ((int64_t)(batch * args.h + head) * args.qtiles + m_block) * (int64_t)args.ktiles;
+    for (int j = threadIdx.x; j < T; j += kFwdThreads) stat_row[seq[j]] = ordered_to_float(stat_s[j]);
+  }
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+}  // namespace la

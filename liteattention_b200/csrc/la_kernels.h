@@ -1,0 +1,54 @@
+// la_kernels.h -- internal interface between the host glue (la_api.cu) and the kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace la {
+
+constexpr int kFwdThreads = 320;        // 8 softmax warps + TMA warp + MMA warp
+constexpr int kFwdMaxTiles = 2048;      // K tiles one CTA can visit (seqlen_k <= 360448)
+constexpr int kFwdSmemBytes = 229632;   // dynamic shared memory of la_fwd_kernel (incl. 1 KB alignment slack)
+
+struct FwdKernelArgs {
+  __nv_bfloat16* out;
+  float* lse;
+  const int32_t* read_list;
+  float* tile_stat;
+  float* dbg;  // bring-up only: raw S of the first visited tile of CTA (dbg_block, 0, 0)
+  int64_t o_batch_stride, o_row_stride, o_head_stride;
+  int32_t h, h_per_kv, seqlen_q, seqlen_k, qtiles, ktiles;
+  int32_t dbg_block;
+  float softmax_scale;  // multiplies raw S
+  float scale_log2;     // softmax_scale * log2(e)
+};
+
+__global__ void la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                              const __grid_constant__ CUtensorMap tmap_v, const FwdKernelArgs args);
+
+struct UpdateKernelArgs {
+  const int32_t* read_list;
+  const int32_t* must_do_list;
+  int32_t* write_list;
+  const float* tile_stat;
+  int32_t* overflow_count;
+  int32_t rows;    // b * h * qtiles
+  int32_t ktiles;
+  float thr;
+};
+
+constexpr int kUpdWarpsPerBlock = 4;
+__global__ void la_skip_update_kernel(const UpdateKernelArgs args);
+size_t la_skip_update_smem_bytes(int ktiles);
+
+struct CombineKernelArgs {
+  const __nv_bfloat16* o_parts[8];
+  const float* lse_parts[8];
+  __nv_bfloat16* out;
+  float* lse;
+  int32_t n_parts, b, h, s, d;
+};
+__global__ void la_combine_kernel(const CombineKernelArgs args);
+
+}  // namespace la

@@ -1,0 +1,188 @@
+// la_skip_update.cu -- QK-Skip mask update for B200 (sm_100a): turns the per-tile statistic emitted by
+// la_fwd_kernel into the next run-length skip list.
+//
+// Restates the behaviour of SkipListWriter + the range loop of the reference's fused kernel
+// (hopper/_internal/cpp/mainloop_fwd_sm90_tma_gmma_ws.hpp:121-192 writer, :1804-1827 loop,
+//  softmax.h:194/207 predicate `any_row((m_loc - m_prev) * scale_log2 > thr)` => "do"):
+//
+//   w = 1; skipping = true; first visited tile: vote = do, never tested, no must-do lookup.
+//   every later visited tile n: vote_skip = !(stat[n] > thr); if vote_skip and n lies inside the current
+//   must-do range (n <= start && n > end, reader advanced by a single `if`) the vote becomes "do";
+//   a change of state writes n; at the end of each READ range the state is forced back to "skipping" and the
+//   inclusive end is written iff the last RAW vote (before the must-do override) was "do"; row[0] = w - 1.
+//
+// This is integer work gated by one fp32 compare per tile, HBM-bound: one warp per (b, h, q-tile) row.
+// Fast path (list sorted descending, no must-do ranges -- the only shape the writer itself produces):
+// lanes map to K tiles, the state machine collapses to neighbour compares + ballot prefix sums.
+// General path (must-do list present, or a hand-made unsorted list): lane 0 walks the row serially.
+//
+// Bounds: the reference writer has no capacity check and can overflow a row into its neighbour
+// (SURVEY.md section 8 a12-iii).  Here a row that would need more than `ktiles` entries is replaced by a
+// copy of the read row (always valid, merely not sparser) and counted in *overflow_count.
+#include "la_kernels.h"
+#include "la_ptx.cuh"
+
+namespace la {
+
+namespace {
+constexpr int kMaskWords = kFwdMaxTiles / 32;
+
+__device__ __forceinline__ int clamp_len(int len, int ktiles) { return min(max(len, 0), ktiles) & ~1; }
+}  // namespace
+
+size_t la_skip_update_smem_bytes(int) { return (size_t)kUpdWarpsPerBlock * 3 * kMaskWords * sizeof(uint32_t); }
+
+__global__ void __launch_bounds__(kUpdWarpsPerBlock * 32) la_skip_update_kernel(const UpdateKernelArgs args) {
+  extern __shared__ uint32_t upd_smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int row_id = blockIdx.x * kUpdWarpsPerBlock + warp;
+  if (row_id >= args.rows) return;
+
+  const int ktiles = args.ktiles;
+  const int64_t stride = (int64_t)ktiles + 1;
+  const int32_t* rd = args.read_list + row_id * stride;
+  const int32_t* md = args.must_do_list ? args.must_do_list + row_id * stride : nullptr;
+  int32_t* wr = args.write_list + row_id * stride;
+  const float* stat = args.tile_stat + (int64_t)row_id * ktiles;
+  const float thr = args.thr;
+
+  const int len = clamp_len(rd[0], ktiles);
+  const int nranges = len >> 1;
+  if (nranges == 0) {
+    if (lane == 0) wr[0] = 0;
+    return;
+  }
+
+  // ---- classify: is the must-do row trivial, is the read row sorted/disjoint?
+  bool general = false;
+  if (md != nullptr) {
+    const int mdlen = md[0];
+    // `[2, 0, 0]` (lite_attention.py:229-231 default) protects nothing: n <= 0 && n > 0 is never true.
+    if (!(mdlen <= 0 || (mdlen == 2 && md[1] == 0 && md[2] == 0))) general = true;
+  }
+  uint32_t* vis = upd_smem + warp * 3 * kMaskWords;
+  uint32_t* smask = vis + kMaskWords;
+  uint32_t* emask = smask + kMaskWords;
+  const int words = (ktiles + 31) >> 5;
+  for (int j = lane; j < words; j += 32) vis[j] = smask[j] = emask[j] = 0u;
+  __syncwarp();
+  int first_n = min(rd[1], ktiles - 1);
+  for (int r0 = 0; r0 < nranges && !general; r0 += 32) {
+    const int r = r0 + lane;
+    bool bad = false;
+    if (r < nranges) {
+      int s = rd[1 + 2 * r], e = rd[2 + 2 * r];
+      s = min(s, ktiles - 1);
+      e = max(e, 0);
+      if (s < e) bad = true;                                   // empty after clamping: leave to the general path
+      if (r > 0 && !(max(rd[2 * r], 0) > s)) bad = true;       // previous end must be strictly above this start
+      if (!bad) {
+        for (int n = e; n <= s;) {                             // set bits [e, s]
+          const int wi = n >> 5, lo = n & 31;
+          const int hi = min(31, s - (wi << 5));
+          const uint32_t m = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+          atomicOr(&vis[wi], m);
+          n = (wi + 1) << 5;
+        }
+        atomicOr(&smask[s >> 5], 1u << (s & 31));
+        atomicOr(&emask[e >> 5], 1u << (e & 31));
+      }
+    }
+    if (__any_sync(0xffffffffu, bad)) general = true;
+  }
+  __syncwarp();
+
+  int w = 1;  // next write slot
+  bool overflow = false;
+
+  if (!general) {
+    // ---------------------------------------------------------------- fast path
+    bool carry_ev = true;  // effective vote of the previous (higher) tile; irrelevant at range starts
+    for (int base = ktiles - 1; base >= 0; base -= 32) {
+      const int n = base - lane;
+      bool v = false, st = false, en = false;
+      if (n >= 0) {
+        const uint32_t bit = 1u << (n & 31);
+        v = vis[n >> 5] & bit;
+        st = smask[n >> 5] & bit;
+        en = emask[n >> 5] & bit;
+      }
+      bool rv = false;  // raw vote: true = skip
+      if (v && n != first_n) rv = !(stat[n] > thr);
+      const bool ev = rv;
+      bool prev_ev = __shfl_up_sync(0xffffffffu, ev, 1);
+      if (lane == 0) prev_ev = carry_ev;
+      const bool ps = st ? true : prev_ev;
+      const bool a = v && (ev != ps);
+      const bool b = v && en && !rv;
+      const uint32_t ma = __ballot_sync(0xffffffffu, a);
+      const uint32_t mb = __ballot_sync(0xffffffffu, b);
+      const uint32_t lt = (1u << lane) - 1u;
+      const int pos = w + __popc(ma & lt) + __popc(mb & lt);
+      if (a && pos <= ktiles) wr[pos] = n;
+      if (b && pos + (a ? 1 : 0) <= ktiles) wr[pos + (a ? 1 : 0)] = n;
+      w += __popc(ma) + __popc(mb);
+      carry_ev = __shfl_sync(0xffffffffu, ev, 31);
+    }
+    overflow = (w - 1) > ktiles;
+  } else {
+    // ---------------------------------------------------------------- general path (lane 0)
+    if (lane == 0) {
+      bool skipping = true, raw = false, first = true;
+      int mdlen = 2, mi = 1, ms = 0, me = 0;
+      auto md_at = [&](int idx) { return (md != nullptr && idx <= ktiles) ? md[idx] : 0; };
+      if (md != nullptr) {
+        mdlen = md[0];
+        ms = md_at(1);
+        me = md_at(2);
+      }
+      auto put = [&](int val) {
+        if (w <= ktiles) wr[w] = val;
+        else overflow = true;
+        ++w;
+      };
+      for (int r = 0; r < nranges; ++r) {
+        int s = min(rd[1 + 2 * r], ktiles - 1);
+        const int e = max(rd[2 + 2 * r], 0);
+        if (s < e) continue;
+        for (int n = s; n >= e; --n) {
+          bool vote;
+          if (first) {
+            vote = false;
+            raw = false;
+            first = false;
+          } else {
+            raw = !(stat[n] > thr);
+            vote = raw;
+            if (vote) {
+              if (me > n && mi <= mdlen) {  // single `if`, not `while` (writer :156-159)
+                mi += 2;
+                ms = md_at(mi);
+                me = md_at(mi + 1);
+              }
+              if (n <= ms && n > me) vote = false;
+            }
+          }
+          if (vote != skipping) {
+            put(n);
+            skipping = vote;
+          }
+        }
+        skipping = true;            // record_range_end gets the RAW vote (Appendix A quirk)
+        if (!raw) put(e);
+      }
+    }
+    w = __shfl_sync(0xffffffffu, w, 0);
+    overflow = __shfl_sync(0xffffffffu, (int)overflow, 0);
+  }
+
+  if (overflow) {
+    for (int j = lane; j <= len; j += 32) wr[j] = (j == 0) ? len : rd[j];
+    if (lane == 0 && args.overflow_count != nullptr) atomicAdd(args.overflow_count, 1);
+  } else if (lane == 0) {
+    wr[0] = w - 1;
+  }
+}
+
+}  // namespace la

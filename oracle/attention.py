@@ -1,0 +1,111 @@
+"""Tile-exact CPU restatement (torch, fp32) of the reference's skippable attention forward.
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+Follows, per (batch, head, 128-row Q tile):
+  first visited tile  : mainloop_fwd_sm90_tma_gmma_ws.hpp:1612-1663  (seqlen mask mask.h:66-76, never skip-tested)
+  every further tile  : mainloop :1667-1755; softmax.h:139-222 (max, rescale, skip predicate :194),
+                        softmax.h:81-121 (P = exp2(S*c - m*c)), :263-273 (row sum in fp32 before bf16 rounding)
+  P -> bf16 (RN) before PV: utils.h:211-225;  fp32 accumulate
+  finalize            : softmax.h:275-296 (O / l, LSE = m*scale + ln l);  epilogue_fwd.hpp:241-242, 298-330
+  list codec          : oracle/skiplist.py
+TMA zero-fill: Q rows >= S and K/V rows >= S are zeros (only the FIRST visited tile gets -inf on cols >= S).
+"""
+import math
+
+import torch
+
+from . import skiplist as sl
+
+LOG2E = 1.4426950408889634
+
+
+def lite_attention_oracle(q, k, v, softmax_scale=None, read_list=None, must_do_list=None, thr=-3.0,
+                          on_overflow="copy"):
+    """q,k,v: (B,S,H,D) bf16 (CPU).  read_list / must_do_list: int32 [>=B,H,qtiles,ktiles+1] or None (dense).
+    Returns dict(out bf16 (B,Sq,H,D), lse fp32 (B,H,Sq), write_list int32 like read_list (or None),
+                 stat fp32 (B,H,qtiles,ktiles) with NaN at unvisited tiles and +inf at each row's first tile,
+                 visited = number of (q-tile,k-tile) pairs computed)."""
+    B, Sq, H, D = q.shape
+    Sk, Hk = k.shape[1], k.shape[2]
+    assert D == 128 and q.dtype == torch.bfloat16
+    bm, bn = sl.get_MN(D, 2)
+    qtiles, ktiles = sl.ceil_div(Sq, bm), sl.ceil_div(Sk, bn)
+    scale = D ** -0.5 if softmax_scale is None else float(softmax_scale)
+    c = torch.tensor(scale, dtype=torch.float32) * torch.tensor(LOG2E, dtype=torch.float32)  # fp32 product, mainloop :760
+    thr32 = torch.tensor(thr, dtype=torch.float32)
+
+    qf = torch.zeros(B, qtiles * bm, H, D)
+    qf[:, :Sq] = q.float()
+    kf = torch.zeros(B, ktiles * bn, Hk, D)
+    kf[:, :Sk] = k.float()
+    vf = torch.zeros(B, ktiles * bn, Hk, D)
+    vf[:, :Sk] = v.float()
+
+    out = torch.zeros(B, Sq, H, D, dtype=torch.bfloat16)
+    lse = torch.full((B, H, Sq), float("-inf"))
+    stat = torch.full((B, H, qtiles, ktiles), float("nan"))
+    write_list = None if read_list is None else read_list.clone()
+    n_visited = 0
+    rep = H // Hk
+    for b in range(B):
+        for h in range(H):
+            hk = h // rep
+            for m in range(qtiles):
+                rd = sl.init_row(ktiles) if read_list is None else read_list[b, h, m].tolist()
+                Qt = qf[b, m * bm:(m + 1) * bm, h]
+                tiles = sl.visited_tiles(rd, ktiles)
+                votes = {}
+                m_run = torch.full((bm,), float("-inf"))
+                l = torch.zeros(bm)
+                O = torch.zeros(bm, D)
+                for idx, n in enumerate(tiles):
+                    Kt = kf[b, n * bn:(n + 1) * bn, hk]
+                    Vt = vf[b, n * bn:(n + 1) * bn, hk]
+                    S_ = Qt @ Kt.T
+                    if idx == 0:
+                        col = torch.arange(n * bn, (n + 1) * bn)
+                        S_[:, col >= Sk] = float("-inf")
+                    m_loc = S_.max(dim=1).values
+                    m_new = torch.maximum(m_run, m_loc)
+                    if idx > 0:
+                        d = (m_loc - m_run) * c
+                        do_rows = d > thr32                      # NaN compares false
+                        votes[n] = not bool(do_rows.any())
+                        dd = torch.where(torch.isnan(d), torch.full_like(d, float("-inf")), d)
+                        stat[b, h, m, n] = dd.max()
+                    else:
+                        stat[b, h, m, n] = float("inf")
+                    m_safe = torch.where(torch.isinf(m_new) & (m_new < 0), torch.zeros_like(m_new), m_new)
+                    alpha = torch.exp2((m_run - m_safe) * c)
+                    P = torch.exp2(S_ * c - (m_safe * c)[:, None])
+                    l = l * alpha + P.sum(dim=1)
+                    O = O * alpha[:, None] + P.to(torch.bfloat16).float() @ Vt
+                    m_run = m_new
+                    n_visited += 1
+                if tiles:
+                    bad = (l == 0) | torch.isnan(l)
+                    inv = torch.where(bad, torch.zeros_like(l), 1.0 / l)
+                    rows = min(bm, Sq - m * bm)
+                    out[b, m * bm:m * bm + rows, h] = (O * inv[:, None])[:rows].to(torch.bfloat16)
+                    ls = torch.where(bad, torch.full_like(l, float("-inf")), m_run * scale + torch.log(l))
+                    lse[b, h, m * bm:m * bm + rows] = ls[:rows]
+                if write_list is not None:
+                    md = None if must_do_list is None else must_do_list[b, h, m].tolist()
+                    row, _ = sl.skip_list_step(rd, lambda n: votes[n], md, ktiles, on_overflow=on_overflow)
+                    write_list[b, h, m, :len(row)] = torch.tensor(row, dtype=torch.int32)
+    return dict(out=out, lse=lse, write_list=write_list, stat=stat, visited=n_visited)
+
+
+def dense_attention_ref(q, k, v, softmax_scale=None):
+    """fp32 reference of plain softmax attention (same math as hopper/tests/test_util.py:226-348
+    attention_ref without masks): q,k,v (B,S,H,D) any float dtype -> (out fp32 (B,S,H,D), lse fp32 (B,H,S))."""
+    D = q.shape[-1]
+    scale = D ** -0.5 if softmax_scale is None else float(softmax_scale)
+    qf, kf, vf = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))
+    if kf.shape[1] != qf.shape[1]:
+        rep = qf.shape[1] // kf.shape[1]
+        kf, vf = kf.repeat_interleave(rep, 1), vf.repeat_interleave(rep, 1)
+    s = (qf @ kf.transpose(-1, -2)) * scale
+    lse = torch.logsumexp(s, dim=-1)
+    o = torch.softmax(s, dim=-1) @ vf
+    return o.permute(0, 2, 1, 3).contiguous(), lse

@@ -130,6 +130,15 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                            ((int64_t)(batch * args.h + head) * args.qtiles + m_block) * (int64_t)(args.ktiles + 1);
       int len = row[0];
       len = min(max(len, 0), args.ktiles) & ~1;
+      if (args.ktiles == 1) {
+        // A one-tile row is [len, 0]: the range end would live in the next row's slot.  The reference
+        // still visits tile 0 (the first listed tile is processed unconditionally, mainloop :1612-1663).
+        len = 0;
+        if (row[0] > 0) {
+          if (lane == 0) seq[0] = 0;
+          count = 1;
+        }
+      }
       for (int r = 0; r < len; r += 2) {
         int s = row[1 + r], e = row[2 + r];
         // The reference does not validate list contents (a malformed list is an OOB tile index there);

@@ -47,6 +47,18 @@ __global__ void __launch_bounds__(kUpdWarpsPerBlock * 32) la_skip_update_kernel(
   const float* stat = args.tile_stat + (int64_t)row_id * ktiles;
   const float thr = args.thr;
 
+  if (ktiles == 1) {
+    // One-tile rows are [len, 0] (no room for a range end): the only tile is always kept.
+    if (lane == 0) {
+      if (rd[0] > 0) {
+        wr[0] = 2;
+        wr[1] = 0;
+      } else {
+        wr[0] = 0;
+      }
+    }
+    return;
+  }
   const int len = clamp_len(rd[0], ktiles);
   const int nranges = len >> 1;
   if (nranges == 0) {

@@ -1,0 +1,293 @@
+"""Stateful wrapper around the B200 QK-Skip attention forward.
+
+Host-side mirror of hopper/lite_attention.py of the reference (class LiteAttention :15-320,
+SeqParallelLiteAttention :322-345): same constructor, call signature, public attributes (`threshold`,
+`enable_skipping`, `_skip_list` [2, max_batch, H, qtiles, ktiles+1] int32, `_phase`), same re-initialisation
+rules and the same list format, so that code written against the reference (README.md:265-323, the Wan
+integration) runs unchanged.  Differences, all documented in DESIGN.md:
+  * `enable_skipping=False` runs the dense kernel (the reference intends that, README.md:159, but raises on
+    `None.shape` because lite_attention.py:262 tests a bound method);
+  * the default (empty) must-do list is not materialised per call (the reference allocates and broadcasts a
+    [max_batch,H,qtiles,ktiles+1] tensor every call, :239-241); the kernel treats "no list" as `[2,0,0]`;
+  * `calc_percentage` keeps the reference's (broken for descending lists, :61-85) formula for drop-in
+    compatibility; `sparsity()` / `last_sparsity` give the correct figure.
+"""
+import os
+from typing import Optional, Tuple, Union
+
+import torch
+
+from .flash_attn_interface import flash_attn_func
+
+
+class LiteAttention:
+    """Attention with temporal-sparse QK-Skip lists managed internally (one object per layer, reused across
+    diffusion timesteps).
+
+    Args:
+        enable_skipping: gate K tiles by the skip list and keep updating it.  Default True.
+        threshold: QK-skip threshold in the exp2 domain (a tile is dropped once every row's largest softmax
+            numerator relative to the running max is <= 2**threshold).  Must be negative unless
+            LITE_ATTENTION_DEBUG is set.  Default -10.0.
+        max_batch_size: leading dimension the list buffers are allocated for.  Default 4.
+    """
+
+    def __init__(self, enable_skipping: bool = True, threshold: float = -10.0, max_batch_size: int = 4):
+        self._skip_list = None
+        self._phase = 0
+
+        self._last_seq_len = None
+        self._last_head_dim = None
+        self._last_v_colmajor = None
+        self._last_dtype = None
+        self._last_device = None
+        self._last_num_heads = None
+
+        self._last_percentage = 0.0
+        self._must_do_cache_key = None
+        self._must_do_cache = None
+
+        self.enable_skipping = enable_skipping
+        self.set_threshold(threshold)
+        self.max_batch_size = max_batch_size
+
+    # ------------------------------------------------------------------ static helpers (reference API)
+    @staticmethod
+    def ceil_div(x, y):
+        return (x + y - 1) // y
+
+    @staticmethod
+    def calc_percentage(read_list: torch.Tensor) -> float:
+        """Reference formula (hopper/lite_attention.py:61-85), kept verbatim in meaning: it was written for
+        ascending lists and returns a NEGATIVE "not skipped" fraction for the descending lists the kernel
+        uses.  Prefer `LiteAttention.sparsity`."""
+        read_list = read_list.to(torch.int64)
+        skip_lengths = read_list[:, :, :, 0] // 2
+        sized = read_list[:, :, :, 2:] - read_list[:, :, :, 1:-1]
+        if sized.shape[-1] % 2 != 0:
+            sized = torch.cat([sized, torch.zeros_like(sized[..., :1])], dim=-1)
+        sized = sized.view(*sized.shape[:3], -1, 2)[..., 0].cumsum(dim=-1)
+        total_possible = read_list.shape[0] * read_list.shape[1] * read_list.shape[2] * (read_list.shape[3] - 1)
+        # gather index len//2 is one past the last range; the reference does the same (clamped here for safety)
+        idx = skip_lengths.clamp(max=sized.shape[-1] - 1).unsqueeze(-1)
+        total_not_skipped = torch.gather(sized, dim=-1, index=idx).squeeze(-1).sum()
+        return total_not_skipped / total_possible if total_possible > 0 else 1.0
+
+    @staticmethod
+    def sparsity(skip_list: torch.Tensor) -> float:
+        """Fraction of (q-tile, k-tile) pairs NOT listed: 1 - sum_ranges(start - end + 1) / ktiles, averaged over
+        rows.  skip_list: [..., ktiles+1] int32 rows of [len, s0, e0, ...]."""
+        rows = skip_list.reshape(-1, skip_list.shape[-1]).to(torch.int64)
+        ktiles = rows.shape[1] - 1
+        ln = rows[:, 0].clamp(0, ktiles)
+        ent = rows[:, 1:]
+        pos = torch.arange(ktiles, device=rows.device)
+        valid = pos[None, :] < ln[:, None]
+        sign = torch.where(pos % 2 == 0, 1, -1)[None, :]           # +start, -end
+        covered = (ent * sign * valid).sum(dim=1) + ln // 2
+        return float(1.0 - covered.double().mean().item() / ktiles)
+
+    @staticmethod
+    def get_MN(head_dim, element_size, v_colmajor=False):
+        """(kBlockM, kBlockN) of the skip-list tiles; same table as the reference (hopper/lite_attention.py:87-111,
+        tile_size.h:10-62).  The list geometry is API, so the B200 kernel gates on these Hopper tile sizes."""
+        if element_size == 2:
+            if head_dim <= 64:
+                return 192, 192
+            elif head_dim <= 96:
+                return 192, 144
+            elif head_dim <= 128:
+                return 128, 176
+            elif head_dim <= 192:
+                return 128, 112
+            else:
+                return 128, 80
+        else:
+            if head_dim <= 64:
+                return 192, 160
+            elif head_dim <= 96:
+                return 192, 128
+            elif head_dim <= 128:
+                return 128, (192 if v_colmajor else 224)
+            elif head_dim <= 192:
+                return 128, 160
+            else:
+                return 128, 128
+
+    @staticmethod
+    def init_skip_list(batch, seq_len, heads, head_dim, v_colmajor, dtype, device, must_skip_list=None) -> torch.Tensor:
+        """[2, batch, heads, qtiles, ktiles+1] int32 double buffer, every row = one range over all K tiles
+        (hopper/lite_attention.py:113-153).  `must_skip_list` (token ranges that are never computed) is the
+        reference's experimental branch (:126-145); it is reproduced without mutating the caller's list."""
+        element_size = dtype.itemsize
+        kTileM, kTileN = LiteAttention.get_MN(head_dim, element_size, v_colmajor)
+        qtiles = LiteAttention.ceil_div(seq_len, kTileM)
+        ktiles = LiteAttention.ceil_div(seq_len, kTileN)
+        skip_list = torch.zeros(2, batch, heads, qtiles, ktiles + 1, dtype=torch.int32, device=device)
+        if must_skip_list is not None:
+            msl = list(must_skip_list)
+            n = msl[0] if msl else 0          # the reference reads element 0 as a length here (:130)
+            for i in range(1, min(n, len(msl) - 1) + 1):
+                if i % 2 == 1:
+                    msl[i] = (msl[i] + kTileN - 1) // kTileN
+                else:
+                    msl[i] = msl[i] // kTileN
+            msl.insert(0, ktiles - 1)
+            msl.append(0)
+            msl.insert(0, len(msl))
+            values = torch.tensor(msl, dtype=torch.int32, device=device)
+            skip_list[:, :, :, :, :len(msl)] = values
+        else:
+            skip_list[:, :, :, :, 1] = ktiles - 1
+            skip_list[:, :, :, :, 0] = 2
+        return skip_list
+
+    def _init_skip_list(self, query, value, must_skip_list=None):
+        batch, seq_len, heads, head_dim = query.shape
+        assert batch <= self.max_batch_size, \
+            "batch size must be less than or equal to max_batch_size (modify max_batch_size in LiteAttention constructor)"
+        v_colmajor = value.shape[-3] == head_dim
+        return LiteAttention.init_skip_list(self.max_batch_size, seq_len, heads, head_dim, v_colmajor,
+                                            query.dtype, query.device, must_skip_list)
+
+    def _get_read_write_lists(self, query, value, must_skip_list=None) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+        """Pick this call's (read, write) halves of the double buffer; (re)initialise on any shape / dtype /
+        device change; flip the phase (hopper/lite_attention.py:165-212)."""
+        if not self.enable_skipping:
+            return None, None
+        current_seq_len = query.shape[1]
+        head_dim = query.shape[-1]
+        current_num_heads = query.shape[2]
+        v_colmajor = value.shape[-3] == head_dim
+        dtype, device = query.dtype, query.device
+        if (self._skip_list is None or self._last_seq_len != current_seq_len
+                or self._skip_list.device != query.device or self._last_head_dim != head_dim
+                or self._last_v_colmajor != v_colmajor or self._last_dtype != dtype
+                or self._last_device != device or self._last_num_heads != current_num_heads):
+            self._skip_list = self._init_skip_list(query, value, must_skip_list)
+            self._phase = 0
+            self._last_seq_len = current_seq_len
+            self._last_head_dim = head_dim
+            self._last_v_colmajor = v_colmajor
+            self._last_dtype = dtype
+            self._last_device = device
+            self._last_num_heads = current_num_heads
+            if os.getenv("LITE_ATTENTION_VERBOSE", "FALSE") != "FALSE":
+                print("[Warning]: reinitialized skip list during the forward pass")
+        if self._phase == 0:
+            read_list, write_list = self._skip_list[0], self._skip_list[1]
+            self._phase = 1
+        else:
+            read_list, write_list = self._skip_list[1], self._skip_list[0]
+            self._phase = 0
+        return read_list, write_list
+
+    @staticmethod
+    def _expand_must_do_list(must_do_list, list_shape, query, value):
+        """1-D token ranges [s0, e0, s1, e1, ...] -> int32 [batch, heads, qtiles, ktiles+1] block-range rows
+        `[len, ceil(s/kN), floor(e/kN), ...]` (hopper/lite_attention.py:214-242; the rounding quirk is kept)."""
+        head_dim = query.shape[-1]
+        v_colmajor = value.shape[-3] == head_dim
+        q_tile_size, k_tile_size = LiteAttention.get_MN(head_dim, query.dtype.itemsize, v_colmajor)
+        must_do_list = [len(must_do_list)] + list(must_do_list)
+        for i in range(1, must_do_list[0] + 1):
+            if i % 2 == 1:
+                must_do_list[i] = (must_do_list[i] + k_tile_size - 1) // k_tile_size
+            else:
+                must_do_list[i] = must_do_list[i] // k_tile_size
+        values = torch.tensor(must_do_list, dtype=torch.int32, device=query.device)
+        values = torch.cat([values, torch.zeros(list_shape[3] - values.size(0), dtype=values.dtype, device=values.device)])
+        return values.repeat(*list_shape[:3], 1).contiguous()
+
+    def _must_do_expanded(self, must_do_list, list_shape, query, value):
+        key = (tuple(must_do_list), tuple(list_shape), query.device, query.dtype, query.shape[-1])
+        if self._must_do_cache_key != key:
+            self._must_do_cache = self._expand_must_do_list(list(must_do_list), list_shape, query, value)
+            self._must_do_cache_key = key
+        return self._must_do_cache
+
+    # ------------------------------------------------------------------ call
+    def __call__(self, query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, scale: Optional[float] = None,
+                 return_softmax_lse: bool = False, must_do_list: list = None,
+                 must_skip_list: list = None) -> Union[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
+        """query/key/value: (batch, seq_len, heads, head_dim) bf16.  Returns the attention output
+        (batch, seq_len, heads, head_dim) [and softmax_lse (batch, heads, seq_len) fp32].
+        must_do_list: token ranges [start0, end0, start1, end1, ...] (descending) that may never be skipped."""
+        read_list, write_list = self._get_read_write_lists(query, value, must_skip_list)
+
+        must_do_list_expanded = None
+        if self.enable_skipping and must_do_list is not None:
+            must_do_list_expanded = self._must_do_expanded(must_do_list, write_list.shape, query, value)
+
+        output = flash_attn_func(q=query, k=key, v=value, softmax_scale=scale, attn_read_list=read_list,
+                                 attn_must_do_list=must_do_list_expanded, attn_write_list=write_list,
+                                 thr=self.threshold, return_softmax_lse=return_softmax_lse)
+
+        if self.enable_skipping and os.getenv("LITE_ATTENTION_VERBOSE", "FALSE") != "FALSE":
+            real_batch_size = query.shape[0]
+            self._last_percentage = 1.0 - LiteAttention.sparsity(read_list[:real_batch_size])
+            print(f"[Info]: Percentage of tiles skipped: {1.0 - self._last_percentage:.2%}")
+        return output
+
+    @property
+    def read_list(self) -> Optional[torch.Tensor]:
+        """The list the NEXT call will read (i.e. the one the last call wrote)."""
+        if self._skip_list is None:
+            return None
+        return self._skip_list[self._phase]
+
+    def last_sparsity(self, batch: Optional[int] = None) -> float:
+        """Sparsity of the list the next call will use."""
+        if self._skip_list is None:
+            return 0.0
+        rl = self.read_list
+        return LiteAttention.sparsity(rl if batch is None else rl[:batch])
+
+    def reset_skip_state(self):
+        """Forget the skip lists (next call starts dense).  hopper/lite_attention.py:293-304."""
+        self._skip_list = None
+        self._phase = 0
+        self._last_seq_len = None
+        self._last_head_dim = None
+        self._last_v_colmajor = None
+        self._last_dtype = None
+        self._last_device = None
+        self.verbose_reinitialization = False
+        self._last_percentage = 0.0
+        self._last_num_heads = None
+
+    def set_threshold(self, threshold: float):
+        """Threshold must be negative unless LITE_ATTENTION_DEBUG is set (hopper/lite_attention.py:306-313)."""
+        if threshold >= 0 and os.getenv("LITE_ATTENTION_DEBUG", "FALSE") == "FALSE":
+            raise ValueError("threshold must be negative when debug mode is not enabled")
+        self.threshold = threshold
+
+    def enable_skip_optimization(self, enable: bool = True):
+        self.enable_skipping = enable
+
+
+class SeqParallelLiteAttention:
+    """`num_nodes` independent LiteAttention states, one per K/V shard (`split_idx`), for callers that shard the
+    sequence and merge partial results by LSE (hopper/lite_attention.py:322-345; merge: flash_attn_combine)."""
+
+    def __init__(self, num_nodes: int, enable_skipping: bool = True, threshold: float = -10.0, max_batch_size: int = 4):
+        self.num_nodes = num_nodes
+        self.lite_attention = [LiteAttention(enable_skipping, threshold, max_batch_size) for _ in range(num_nodes)]
+        self.set_threshold(threshold)
+
+    def __call__(self, query, key, value, split_idx: int, scale: Optional[float] = None,
+                 return_softmax_lse: bool = False):
+        assert split_idx < self.num_nodes, "split_idx must be less than num_nodes"
+        return self.lite_attention[split_idx](query, key, value, scale, return_softmax_lse)
+
+    def reset_skip_state(self):
+        for la in self.lite_attention:
+            la.reset_skip_state()
+
+    def set_threshold(self, threshold: float):
+        for la in self.lite_attention:
+            la.set_threshold(threshold)
+
+    def enable_skip_optimization(self, enable: bool = True):
+        for la in self.lite_attention:
+            la.enable_skip_optimization(enable)

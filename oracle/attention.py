@@ -22,7 +22,7 @@ LOG2E = 1.4426950408889634
 def lite_attention_oracle(q, k, v, softmax_scale=None, read_list=None, must_do_list=None, thr=-3.0,
                           on_overflow="copy"):
     """q,k,v: (B,S,H,D) bf16 (CPU).  read_list / must_do_list: int32 [>=B,H,qtiles,ktiles+1] or None (dense).
-    Returns dict(out bf16 (B,Sq,H,D), lse fp32 (B,H,Sq), write_list int32 like read_list (or None),
+    Returns dict(out bf16 (B,Sq,H,D), out_f32 (the same before the final bf16 rounding), lse fp32 (B,H,Sq), write_list int32 like read_list (or None),
                  stat fp32 (B,H,qtiles,ktiles) with NaN at unvisited tiles and +inf at each row's first tile,
                  visited = number of (q-tile,k-tile) pairs computed)."""
     B, Sq, H, D = q.shape
@@ -42,6 +42,7 @@ def lite_attention_oracle(q, k, v, softmax_scale=None, read_list=None, must_do_l
     vf[:, :Sk] = v.float()
 
     out = torch.zeros(B, Sq, H, D, dtype=torch.bfloat16)
+    out_f32 = torch.zeros(B, Sq, H, D)
     lse = torch.full((B, H, Sq), float("-inf"))
     stat = torch.full((B, H, qtiles, ktiles), float("nan"))
     write_list = None if read_list is None else read_list.clone()
@@ -86,6 +87,7 @@ def lite_attention_oracle(q, k, v, softmax_scale=None, read_list=None, must_do_l
                     bad = (l == 0) | torch.isnan(l)
                     inv = torch.where(bad, torch.zeros_like(l), 1.0 / l)
                     rows = min(bm, Sq - m * bm)
+                    out_f32[b, m * bm:m * bm + rows, h] = (O * inv[:, None])[:rows]
                     out[b, m * bm:m * bm + rows, h] = (O * inv[:, None])[:rows].to(torch.bfloat16)
                     ls = torch.where(bad, torch.full_like(l, float("-inf")), m_run * scale + torch.log(l))
                     lse[b, h, m * bm:m * bm + rows] = ls[:rows]
@@ -93,7 +95,7 @@ def lite_attention_oracle(q, k, v, softmax_scale=None, read_list=None, must_do_l
                     md = None if must_do_list is None else must_do_list[b, h, m].tolist()
                     row, _ = sl.skip_list_step(rd, lambda n: votes[n], md, ktiles, on_overflow=on_overflow)
                     write_list[b, h, m, :len(row)] = torch.tensor(row, dtype=torch.int32)
-    return dict(out=out, lse=lse, write_list=write_list, stat=stat, visited=n_visited)
+    return dict(out=out, out_f32=out_f32, lse=lse, write_list=write_list, stat=stat, visited=n_visited)
 
 
 def dense_attention_ref(q, k, v, softmax_scale=None):

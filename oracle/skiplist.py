@@ -54,6 +54,8 @@ def visited_tiles(read_row, ktiles=None):
     """Tiles the forward visits for this row, in order (mainloop :1804-1827).  With ktiles given, ranges are
     clamped the way the CUDA kernel clamps them (the reference does not validate list contents)."""
     ln = read_row[0]
+    if ktiles == 1:          # one-tile rows are [len, 0]: no room for the range end, tile 0 is always visited
+        return [0] if ln > 0 else []
     if ktiles is not None:
         ln = min(max(ln, 0), ktiles) & ~1
     out = []
@@ -83,6 +85,8 @@ def skip_list_step(read_row, vote_skip, must_do_row=None, ktiles=None, on_overfl
     """
     if ktiles is None:
         ktiles = len(read_row) - 1
+    if ktiles == 1:
+        return ([2, 0], [0]) if read_row[0] > 0 else ([0], [])
     md = list(must_do_row) if must_do_row is not None else [2, 0, 0]
 
     def md_at(i):

@@ -1,0 +1,359 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the hot path (BASELINE.json): QK-Skip self-attention forward at the
+Wan2.1-14B shape (B=1 per GPU, S=75600, H=40, D=128, bf16) at 42 % tile sparsity, one step = one pass of the
+hot path (skip-list-gated forward + skip-list update) over one batch of synthetic Q/K/V.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--sparsity 0.42]
+    torchrun ... bench.py --gpus N ...          (one rank per GPU, batch-parallel, O gathered to rank 0 over NCCL)
+
+Prints ONE JSON line (rank 0).  `value` = effective TFLOP/s = dense FLOPs (4*B*H*S^2*D, summed over ranks) /
+step time, inputs resident in HBM.  `e2e` = the same through LiteAttention.__call__ with pinned HOST buffers
+(H2D of q/k/v and D2H of O inside the timed region, double-buffered).  `roofline` = executed tensor FLOPs of
+la_fwd_kernel per launch / its CUDA-event duration against the measured bf16 peak.  `cpu_baseline` / `--impl
+reference` = torch SDPA on the host cores on a bounded slice of the same workload (the reference's CPU path
+has no sparse mode: it always does the dense problem).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+S_WAN, H_WAN, D_WAN = 75600, 40, 128          # 21 x 45 x 80 tokens (720p x 81 frames), Wan2.1/2.2-14B
+METRIC = "self_attn_effective_tflops_s75600_d128_sparsity42"
+UNIT = "TFLOP/s (dense-equivalent: 4*B*H*S^2*D / step time)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sparsity", type=float, default=0.42)
+    ap.add_argument("--seq", type=int, default=S_WAN)
+    ap.add_argument("--heads", type=int, default=H_WAN)
+    ap.add_argument("--groups", type=int, default=0, help="head groups for the gather pipeline (0 = auto)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="also time sparsity 0/21/42/57/77 % (kernel only)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_sdpa_sample(seq, steps, warmup, rows=4096):
+    """The reference's CPU path for this op: torch.nn.functional.scaled_dot_product_attention on the host cores.
+    Bounded sample: 1 head, `rows` query rows against all `seq` keys, d=128, fp32 math (dense; no sparse mode)."""
+    import torch
+    import torch.nn.functional as F
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(0)
+    q = torch.randn(1, 1, rows, D_WAN, generator=g)
+    k = torch.randn(1, 1, seq, D_WAN, generator=g)
+    v = torch.randn(1, 1, seq, D_WAN, generator=g)
+    for _ in range(warmup):
+        F.scaled_dot_product_attention(q, k, v)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        F.scaled_dot_product_attention(q, k, v)
+    dt = (time.perf_counter() - t0) / steps
+    flops = 4.0 * rows * seq * D_WAN
+    return {"tflops": flops / dt / 1e12, "sec_per_sample": dt, "cores": torch.get_num_threads(),
+            "sample": f"torch SDPA (CPU, fp32, dense): 1 head x {rows} query rows x {seq} keys x d=128 per step, "
+                      f"{steps} steps after {warmup} warm-up"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 10))
+    r = cpu_sdpa_sample(args.seq, steps, max(1, min(args.warmup, 2)))
+    dense = 4.0 * args.heads * args.seq * float(args.seq) * D_WAN
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["tflops"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": max(1, min(args.warmup, 2)),
+        "ms_per_step": dense / (r["tflops"] * 1e12) * 1e3,      # extrapolated to one full B=1 call
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"Wan2.1-14B self-attention shape B=1 S={args.seq} H={args.heads} D=128, dense on CPU "
+                               "(the reference's CPU path, torch SDPA, has no QK-Skip mode); bounded slice, see "
+                               "cpu_baseline.sample"},
+        "cpu_baseline": {"value": r["tflops"], "unit": UNIT, "cores": r["cores"], "kind": "reference",
+                         "sample": r["sample"]},
+        "e2e": {"value": r["tflops"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                       "-i", str(self.gpu), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"error": "nvidia-smi unavailable"}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.f.read().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+                pw.append(float(parts[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"error": "no samples"}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from liteattention_b200 import LiteAttention, _native, synth
+    from liteattention_b200.dist import BatchParallelLiteAttention
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus and rank == 0:
+        print(f"[bench] warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+
+    B, S, H, D = 1, args.seq, args.heads, D_WAN
+    qt, kt = synth.tile_counts(S)
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    q, k, v = (torch.randn(B, S, H, D, device=dev, generator=g).to(torch.bfloat16) for _ in range(3))
+    dense_flops = synth.flops_dense(B, H, S, S, D)
+
+    def make_list(sp, heads, seed):
+        if sp <= 0:
+            return LiteAttention.init_skip_list(B, S, heads, D, False, torch.bfloat16, dev)[0]
+        rl, _ = synth.exact_sparsity_list(B, heads, qt, kt, sp, seed=seed, device=dev)
+        return rl
+
+    # ---- kernel-level timing: forward + update as two C-ABI calls with CUDA events around each ------------
+    def time_kernels(sp, steps, warmup):
+        rl = make_list(sp, H, seed=1234)
+        wl = torch.zeros_like(rl)
+        out = torch.empty_like(q)
+        lse = torch.empty(B, H, S, device=dev, dtype=torch.float32)
+        stat = torch.empty(B, H, qt, kt, device=dev, dtype=torch.float32)
+        scale = D ** -0.5
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+        for _ in range(warmup):
+            _native.fwd(q, k, v, out, lse, scale, rl, stat)
+            _native.skip_update(rl, None, wl, stat, B, H, qt, kt, float("-inf"))
+        torch.cuda.synchronize()
+        for i in range(steps):
+            ev[i][0].record()
+            _native.fwd(q, k, v, out, lse, scale, rl, stat)
+            ev[i][1].record()
+            _native.skip_update(rl, None, wl, stat, B, H, qt, kt, float("-inf"))
+            ev[i][2].record()
+        torch.cuda.synchronize()
+        assert torch.equal(wl[..., 0], rl[..., 0])              # thr = -inf: the list is stationary
+        fwd_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in ev)
+        upd_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in ev)
+        return {"sparsity": LiteAttention.sparsity(rl), "fwd_ms": fwd_ms, "update_ms": upd_ms,
+                "exec_flops": synth.flops_executed(rl, S, S, D), "rl": rl}
+
+    # ---- the step the contract times: public objects, batch-parallel, O gathered to rank 0 ----------------
+    n_groups = args.groups if args.groups > 0 else (1 if world == 1 else 5)
+
+    def factory():
+        return LiteAttention(enable_skipping=True, threshold=float("-inf"), max_batch_size=B)
+    bp = BatchParallelLiteAttention(factory, num_heads=H, num_groups=n_groups, dst=0)
+    for gi, gsl in enumerate(bp.groups):                         # preset every head group's list at the target sparsity
+        bp.attn[gi].load_skip_list(make_list(args.sparsity, gsl.stop - gsl.start, seed=1234 + gi), q[:, :, gsl], v[:, :, gsl])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        bp(q, k, v)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _native.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        bp(q, k, v)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = _native.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    stats_t = torch.tensor([ms, float(launches)], device=dev, dtype=torch.float64)
+    if world > 1:
+        mx = stats_t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats_t.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, launches = float(mx[0]), int(sm[1])
+    step_sparsity = statistics.mean(a.last_sparsity(B) for a in bp.attn)
+
+    # ---- end to end through LiteAttention.__call__ with pinned host buffers ---------------------------------
+    e2e = None
+    if not args.no_e2e:
+        hq, hk, hv = (t.cpu().pin_memory() for t in (q, k, v))
+        ho = torch.empty(B, S, H, D, dtype=torch.bfloat16).pin_memory()
+        dbuf = [[torch.empty_like(q) for _ in range(3)] for _ in range(2)]
+        la = factory()
+        la.load_skip_list(make_list(args.sparsity, H, seed=1234), q, v)
+        cs, osr = torch.cuda.Stream(), torch.cuda.Stream()
+        main_s = torch.cuda.current_stream()
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_done = [torch.cuda.Event() for _ in range(2)]
+        keep = [None, None]
+
+        def e2e_step(i):
+            b_ = i & 1
+            cs.wait_event(ev_done[b_])                           # buffer b_ free again (compute of step i-2 finished)
+            with torch.cuda.stream(cs):
+                for dst_, src_ in zip(dbuf[b_], (hq, hk, hv)):
+                    dst_.copy_(src_, non_blocking=True)
+                ev_in[b_].record(cs)
+            main_s.wait_event(ev_in[b_])
+            o = la(*dbuf[b_])
+            ev_done[b_].record(main_s)
+            osr.wait_event(ev_done[b_])
+            with torch.cuda.stream(osr):
+                ho.copy_(o, non_blocking=True)
+            o.record_stream(osr)
+            keep[b_] = o
+        for i in range(max(2, min(args.warmup, 3))):
+            e2e_step(i)
+        main_s.wait_stream(cs)
+        main_s.wait_stream(osr)
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            e2e_step(i)
+        main_s.wait_stream(cs)
+        main_s.wait_stream(osr)
+        e1.record()
+        barrier()
+        e2e_ms = e0.elapsed_time(e1) / args.steps
+        if world > 1:
+            t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t[0])
+        e2e = {"value": dense_flops * world / (e2e_ms * 1e-3) / 1e12, "unit": UNIT, "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": 3 * q.numel() * 2 * world, "d2h_bytes_per_step": q.numel() * 2 * world,
+               "api": "LiteAttention.__call__ on pinned host q/k/v -> host O, double-buffered copies"}
+        del hq, hk, hv, ho, dbuf, keep
+
+    # ---- roofline of the dominant kernel (rank 0), sweep, CPU baseline -------------------------------------
+    line = None
+    if rank == 0:
+        peaks = {}
+        pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk_path):
+            peaks = json.load(open(pk_path))
+        peak_sust = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak_burst = peaks.get("bf16_tflops", 1590.0)
+        kt_main = time_kernels(args.sparsity, args.steps, args.warmup)
+        achieved = kt_main["exec_flops"] / (kt_main["fwd_ms"] * 1e-3) / 1e12
+        traffic = None
+        tr_path = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tr_path):
+            traffic = json.load(open(tr_path)).get("la_fwd_kernel", {}).get("dram_bytes_per_launch")
+        roofline = {"bound": "tensor", "kernel": "la_fwd_kernel", "achieved": achieved, "peak": peak_sust,
+                    "unit": "TFLOP/s", "frac": achieved / peak_sust, "traffic": traffic,
+                    "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+                                    if peaks else "fallback"),
+                    "frac_of_burst_peak": achieved / peak_burst, "kernel_ms": kt_main["fwd_ms"],
+                    "exec_flops_per_launch": kt_main["exec_flops"],
+                    "update_kernel": {"ms": kt_main["update_ms"], "bound": "hbm"}}
+        sweep = None
+        if args.sweep:
+            sweep = []
+            for sp in (0.0, 0.21, 0.42, 0.57, 0.77):
+                r = time_kernels(sp, max(5, args.steps // 2), 3)
+                sweep.append({"sparsity": round(r["sparsity"], 4), "fwd_ms": r["fwd_ms"], "update_ms": r["update_ms"],
+                              "effective_tflops": dense_flops / (r["fwd_ms"] + r["update_ms"]) / 1e9,
+                              "executed_tflops": r["exec_flops"] / r["fwd_ms"] / 1e9})
+        cpu = None
+        if not args.no_cpu and world == 1:
+            c = cpu_sdpa_sample(S, 8, 1)
+            cpu = {"value": c["tflops"], "unit": UNIT, "cores": c["cores"], "kind": "reference", "sample": c["sample"]}
+        line = {
+            "metric": METRIC, "value": dense_flops * world / (ms * 1e-3) / 1e12, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"Wan2.1-14B self-attention shape, B={B} per GPU, S={S}, H={H}, D={D}, bf16; "
+                                   f"fixed random tile Skip-Mask at {step_sparsity:.1%} sparsity (128x176 tiles, runs of "
+                                   "4), thr=-inf so the list is stationary; step = skip-list-gated forward + skip-list "
+                                   "update" + ("" if world == 1 else f"; batch-parallel, O gathered to rank 0 over NCCL "
+                                                                      f"in {n_groups} head groups"),
+                       "batch_per_gpu": B, "seq_len": S, "heads": H, "head_dim": D, "sparsity": step_sparsity,
+                       "parallelism": f"batch-parallel x{world}",
+                       "l2": "q/k/v/o = 3.1 GB per step >> 126 MB L2, no flush needed"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if sweep is not None:
+            line["sweep"] = sweep
+        line["derived_hopper_reference_ms"] = {"0%": 174, "42%": 104.5, "77%": 40.8,
+                                               "note": "derived from README totals (BASELINE.md), H100-class, not measured"}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

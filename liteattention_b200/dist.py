@@ -1,0 +1,89 @@
+"""Batch-parallel multi-GPU driver: one process per GPU, each rank owns whole prompts (its Q/K/V and its
+per-layer skip state, never communicated); the only collective is the gather of O over NVLink
+(the reference has no distributed code on this path at all --
+`grep torch.distributed hopper/` is empty, SeqParallelLiteAttention is bookkeeping only).
+
+To keep the gather off the critical path the heads are processed in groups: the attention kernel of head
+group g+1 runs on the compute stream while group g's O slab is gathered on a side stream.  Only the last
+group's gather is exposed.  The attention callable is injectable so the sharding / pipelining logic can be
+exercised on CPU with the gloo backend (tests/test_dist_cpu.py).
+"""
+from typing import Callable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def shard_batch(n_items: int, world_size: int, rank: int):
+    """Contiguous batch shard [lo, hi) of rank `rank` (prompts are independent: no data-path collective)."""
+    base, rem = divmod(n_items, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def head_groups(num_heads: int, num_groups: int) -> List[slice]:
+    num_groups = max(1, min(num_groups, num_heads))
+    base, rem = divmod(num_heads, num_groups)
+    out, lo = [], 0
+    for g in range(num_groups):
+        hi = lo + base + (1 if g < rem else 0)
+        out.append(slice(lo, hi))
+        lo = hi
+    return out
+
+
+class BatchParallelLiteAttention:
+    """Per-rank LiteAttention state + pipelined gather of O to `dst`.
+
+    attn_factory() must return a callable (q, k, v) -> O for one head group (a LiteAttention object on GPU; each
+    head group keeps its own skip state because lists are indexed [batch, head, qtile]).
+    """
+
+    def __init__(self, attn_factory: Callable[[], Callable], num_heads: int, num_groups: int = 5, dst: int = 0,
+                 group: Optional[dist.ProcessGroup] = None, gather: bool = True):
+        self.groups = head_groups(num_heads, num_groups)
+        self.attn = [attn_factory() for _ in self.groups]
+        self.dst = dst
+        self.pg = group
+        self.gather = gather and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._comm_stream = None
+        self._recv = None          # on dst: per group, list over ranks of [B, S, Hg, D] buffers (reused)
+
+    def _streams(self, device):
+        if device.type == "cuda" and self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=device)
+        return self._comm_stream
+
+    def __call__(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor):
+        """q, k, v: this rank's (B_local, S, H, D).  Returns (local O slabs per head group,
+        gathered) where `gathered` is, on `dst`, a list over head groups of lists over ranks of
+        (B_local, S, Hg, D) tensors (None elsewhere / when not gathering)."""
+        cuda = q.device.type == "cuda"
+        comm = self._streams(q.device)
+        outs, works = [], []
+        if self.gather and self.rank == self.dst and self._recv is None:
+            self._recv = [[torch.empty((q.shape[0], q.shape[1], g.stop - g.start, q.shape[3]), dtype=q.dtype,
+                                       device=q.device) for _ in range(self.world)] for g in self.groups]
+        for gi, g in enumerate(self.groups):
+            o = self.attn[gi](q[:, :, g], k[:, :, g], v[:, :, g])
+            o = o if o.is_contiguous() else o.contiguous()
+            outs.append(o)
+            if not self.gather:
+                continue
+            recv = self._recv[gi] if self.rank == self.dst else None
+            if cuda:
+                ev = torch.cuda.Event()
+                ev.record()
+                comm.wait_event(ev)
+                with torch.cuda.stream(comm):
+                    works.append(dist.gather(o, recv, dst=self.dst, group=self.pg, async_op=True))
+                o.record_stream(comm)
+            else:
+                works.append(dist.gather(o, recv, dst=self.dst, group=self.pg, async_op=True))
+        for w in works:
+            w.wait()
+        if cuda and self.gather:
+            torch.cuda.current_stream(q.device).wait_stream(comm)
+        return outs, (self._recv if (self.gather and self.rank == self.dst) else None)

@@ -243,6 +243,23 @@ class LiteAttention:
         rl = self.read_list
         return LiteAttention.sparsity(rl if batch is None else rl[:batch])
 
+    def load_skip_list(self, skip_list: torch.Tensor, query: torch.Tensor, value: torch.Tensor):
+        """Extension (not in the reference): start from a given list instead of the dense initial one, e.g. a list
+        exported from an earlier run or synthesised at a target sparsity.  skip_list: int32
+        [batch <= max_batch_size, heads, qtiles, ktiles+1] for the geometry of `query`."""
+        buf = self._init_skip_list(query, value)
+        assert skip_list.shape[1:] == buf.shape[2:] and skip_list.shape[0] <= buf.shape[1], \
+            f"skip_list shape {tuple(skip_list.shape)} does not match {tuple(buf.shape[1:])}"
+        buf[:, :skip_list.shape[0]] = skip_list.to(device=buf.device, dtype=torch.int32)
+        self._skip_list = buf
+        self._phase = 0
+        self._last_seq_len = query.shape[1]
+        self._last_head_dim = query.shape[-1]
+        self._last_v_colmajor = value.shape[-3] == query.shape[-1]
+        self._last_dtype = query.dtype
+        self._last_device = query.device
+        self._last_num_heads = query.shape[2]
+
     def reset_skip_state(self):
         """Forget the skip lists (next call starts dense).  hopper/lite_attention.py:293-304."""
         self._skip_list = None

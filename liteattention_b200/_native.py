@@ -67,8 +67,6 @@ def lib():
         L.la_skip_update_sm100.argtypes = [ctypes.POINTER(UpdateParams), _c_vp]
         L.la_fwd_skip_sm100.argtypes = [ctypes.POINTER(FwdParams), ctypes.POINTER(UpdateParams), _c_vp]
         L.la_combine_sm100.argtypes = [ctypes.POINTER(CombineParams), _c_vp]
-        L.la_debug_set.argtypes = [_c_vp, ctypes.c_int]
-        L.la_debug_set.restype = None
         L.la_watchdog_read.argtypes = [ctypes.POINTER(ctypes.c_uint * 4)]
         if L.la_abi_version() != 1:
             raise RuntimeError("libliteattn_b200.so ABI version mismatch")
@@ -163,10 +161,6 @@ def combine(o_parts, lse_parts, out, lse):
 
 def launch_count():
     return int(lib().la_launch_count())
-
-
-def debug_set(dbg_tensor, block=0):
-    lib().la_debug_set(_ptr(dbg_tensor), block)
 
 
 def watchdog_read():

@@ -15,8 +15,6 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
-float* g_dbg_ptr = nullptr;
-int g_dbg_block = 0;
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -106,11 +104,16 @@ int la_get_tile_mn(int head_dim, int element_size, int v_colmajor, int* block_m,
   return (element_size == 2 && head_dim == LA_HEAD_DIM) ? LA_OK : LA_ERR_UNSUPPORTED;
 }
 
-// Bring-up hook (not part of the documented ABI): dump raw S of the first visited tile of CTA (block,0,0).
-void la_debug_set(float* dbg, int block) {
-  g_dbg_ptr = dbg;
-  g_dbg_block = block;
+#ifdef LA_PROFILE_CLOCKS
+int la_prof_read(unsigned long long out[16], int reset) {
+  LA_CUDA(cudaMemcpyFromSymbol(out, la::g_la_prof, 16 * sizeof(unsigned long long)));
+  if (reset) {
+    unsigned long long z[16] = {0};
+    LA_CUDA(cudaMemcpyToSymbol(la::g_la_prof, z, sizeof(z)));
+  }
+  return LA_OK;
 }
+#endif
 
 int la_watchdog_read(unsigned int out[4]) {
   LA_CUDA(cudaMemcpyFromSymbol(out, la::g_la_watchdog, 4 * sizeof(unsigned int)));
@@ -160,8 +163,6 @@ int la_fwd_sm100(const la_fwd_params* p, void* stream_) {
   a.lse = p->lse;
   a.read_list = p->read_list;
   a.tile_stat = p->tile_stat;
-  a.dbg = g_dbg_ptr;
-  a.dbg_block = g_dbg_block;
   a.o_batch_stride = p->o_batch_stride;
   a.o_row_stride = p->o_row_stride;
   a.o_head_stride = p->o_head_stride;

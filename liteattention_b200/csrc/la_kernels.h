@@ -16,10 +16,8 @@ struct FwdKernelArgs {
   float* lse;
   const int32_t* read_list;
   float* tile_stat;
-  float* dbg;  // bring-up only: raw S of the first visited tile of CTA (dbg_block, 0, 0)
   int64_t o_batch_stride, o_row_stride, o_head_stride;
   int32_t h, h_per_kv, seqlen_q, seqlen_k, qtiles, ktiles;
-  int32_t dbg_block;
   float softmax_scale;  // multiplies raw S
   float scale_log2;     // softmax_scale * log2(e)
 };

@@ -47,24 +47,29 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 #endif
 __device__ unsigned int g_la_watchdog[4];  // [0]=flag, [1]=site id, [2]=blockIdx.x, [3]=parity|iter
 
+__device__ __noinline__ void la_watchdog_fail(int site, int iter, uint32_t parity) {
+  if (atomicExch(&g_la_watchdog[0], 1u) == 0u) {
+    g_la_watchdog[1] = (unsigned)site;
+    g_la_watchdog[2] = blockIdx.x;
+    g_la_watchdog[3] = ((unsigned)iter << 1) | parity;
+    __threadfence_system();
+  }
+  __trap();
+}
+
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int site = 0, int iter = 0) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > LA_WATCHDOG_SPINS) {
-      if (atomicExch(&g_la_watchdog[0], 1u) == 0u) {
-        g_la_watchdog[1] = (unsigned)site;
-        g_la_watchdog[2] = blockIdx.x;
-        g_la_watchdog[3] = ((unsigned)iter << 1) | parity;
-        __threadfence_system();
-      }
-      __trap();
-    }
+    if (++spins > LA_WATCHDOG_SPINS) la_watchdog_fail(site, iter, parity);  // cold, out of line (I-cache)
   }
 }
 
 // ----------------------------------------------------------------------------- named barriers
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // ----------------------------------------------------------------------------- TMA
@@ -181,6 +186,31 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// ---- packed 2 x fp32 math (FFMA2 / FADD2 on sm_100a) -------------------------------------------------
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
 // order-preserving float -> int map (NaN must be filtered by the caller)
 __device__ __forceinline__ int float_to_ordered(float f) {
   int i = __float_as_int(f);

@@ -9,22 +9,23 @@
 //   reduced over the tile's 128 rows, which la_skip_update.cu turns into the next list.
 //
 // How (B200-first, nothing shared with the Hopper kernel):
-//   * 10 warps: 2 softmax warpgroups, 1 TMA producer warp, 1 tcgen05 issuer warp.
+//   * 10 warps: 8 softmax warps (two warpgroups that split the 176 S columns 88/88, one TMEM lane = one
+//     query row per thread), 1 TMA producer warp, 1 tcgen05 issuer warp.
 //   * Q (128x128), K and V tiles (176x128, 2 stages each) are TMA-loaded into 128B-swizzled smem.
-//   * S = Q K^T : tcgen05.mma kind::f16, M=128 N=176 K=16 x8, SS operands, fp32 accumulator in TMEM.
+//   * S = Q K^T : tcgen05.mma kind::f16, M=128 N=176 K=16 x8, SS operands, fp32 accumulator in TMEM;
+//     two S buffers so QK^T of tile i+1 runs under the softmax of tile i.
 //   * P (bf16) is written back over S in TMEM and fed to O += P V as the TMEM A operand
 //     (M=128 N=128 K=16 x11, V is the MN-major smem B operand); O lives in TMEM for the whole CTA.
 //   * TMEM map (512 columns allocated): S0 @0, S1 @176, O @352..479.
-//   * Tile ping-pong: warpgroup A owns the even visited tiles (S buffer 0), warpgroup B the odd ones
-//     (S buffer 1); one thread = one query row (TMEM lane) over all 176 columns, in two passes over TMEM
-//     (pass 1 row max, pass 2 exp2 / row sum / bf16 P).  While A's tile is in the tensor pipe (PV, next QK^T)
-//     B's tile is in the MUFU/FMA pipes and vice versa; the running row max travels A -> B -> A through
-//     shared memory + 64-thread named barriers.  (ncu on the first version -- both warpgroups on the same
-//     tile -- showed MUFU idle during every max/exchange phase and the tensor pipe at 53 %.)
-//   * exp2: MUFU.EX2 is exactly as expensive as the two MMAs at d=128 (16 ex2/clk/SM vs 8192 MAC/clk/SM), so
-//     kPolyPairs of every 8 column pairs are evaluated on the FMA pipe instead (Cody-Waite + degree-3
-//     minimax polynomial, packed f32x2 math, relative error 7.5e-5 -- below bf16 rounding of P).
 //   * O is rescaled in TMEM only when some row max of the warp actually moved (exact, not lazy).
+//   * Softmax math is packed (FFMA2 / FADD2 / FMNMX3) and S is read from TMEM exactly once.
+//
+// Why this organisation (measured, see profiles/README.md): at the Wan shape the kernel runs AT THE 1 kW POWER
+// CAP (sw_power_cap active, ~1.6 GHz), so sustained throughput is set by energy per tile, not by schedule
+// tightness.  Two re-organisations that overlap the softmax phases better (tile ping-pong between warpgroups
+// with a two-pass TMEM softmax, then 16 softmax warps; both with part of exp2 moved to the FMA pipe) were
+// built, verified and measured: they raise the work per tile (second TMEM pass, polynomial exp2) and lose
+// 3-6 % sustained throughput against this version, which does the least work per tile.
 #include <cuda_bf16.h>
 
 #include "la_kernels.h"
@@ -33,20 +34,13 @@
 
 namespace la {
 
-#ifdef LA_PROFILE_CLOCKS
-__device__ unsigned long long g_la_prof[16];
-#define LA_CLK(var) const long long var = clock64()
-#define LA_ACC(idx, a, b) prof_acc[idx] += (b) - (a)
-#else
-#define LA_CLK(var)
-#define LA_ACC(idx, a, b)
-#endif
-
 namespace {
 
 constexpr int kM = 128;        // query rows per CTA
 constexpr int kN = 176;        // key rows per tile (skip-list granularity, tile_size.h:35-40)
 constexpr int kD = 128;        // head dim
+constexpr int kHalfN = kN / 2; // S columns per softmax warpgroup
+constexpr int kSoftmaxThreads = 256;
 constexpr int kProducerWarp = 8;
 constexpr int kMmaWarp = 9;
 
@@ -59,9 +53,9 @@ constexpr uint32_t kOffQ = 0;
 constexpr uint32_t kOffK = kOffQ + kQBytes;
 constexpr uint32_t kOffV = kOffK + 2 * kKVBytes;
 constexpr uint32_t kOffBar = kOffV + 2 * kKVBytes;
-constexpr uint32_t kOffMbox = kOffBar + 256;          // float[2][128]  running max mailbox (A->B, B->A)
-constexpr uint32_t kOffFin = kOffMbox + 2 * kM * 4;   // float[2][2][128] final (l, m_ref) per warpgroup
-constexpr uint32_t kOffStat = kOffFin + 4 * kM * 4;
+constexpr uint32_t kOffXchg = kOffBar + 256;
+constexpr uint32_t kOffLx = kOffXchg + 2 * kSoftmaxThreads * 4;
+constexpr uint32_t kOffStat = kOffLx + kSoftmaxThreads * 4;
 constexpr uint32_t kOffSeq = kOffStat + kFwdMaxTiles * 4;
 constexpr uint32_t kSmemUsed = kOffSeq + kFwdMaxTiles * 2;
 static_assert(kSmemUsed + 1024 <= 232448, "shared memory budget (227 KB) exceeded");
@@ -75,9 +69,8 @@ enum Bar : uint32_t {
   kBarVEmpty = 7,
   kBarSFull = 9,   // +buf
   kBarPFull = 11,  // +buf
-  kBarPvDone = 13, // one completion per visited tile
-  kBarOFinal = 14, // completes once, after the last PV
-  kNumBars = 15
+  kBarPvDone = 13,
+  kNumBars = 14
 };
 
 constexpr uint32_t kTmemCols = 512;
@@ -87,65 +80,11 @@ constexpr uint32_t kTmemO = 2 * kN;   // 352
 constexpr uint32_t kIdescQK = make_idesc_bf16(kM, kN, /*b_mn_major=*/0);
 constexpr uint32_t kIdescPV = make_idesc_bf16(kM, kD, /*b_mn_major=*/1);
 
-// exp2 on the FMA pipe for these column pairs of every 8 (bit p set => pair p of the group uses the polynomial)
-#ifndef LA_POLY_MASK
-#define LA_POLY_MASK 0x94u   // pairs 2, 4, 7 -> 3/8 of the elements
-#endif
-constexpr uint32_t kPolyMask = LA_POLY_MASK;
-
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);  // .x (low 16 bits) = lo
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-
-// 2^t for a pair, t <= 0, on the FMA pipe: n = round(t) via the 1.5*2^23 trick, r = t - n in [-0.5, 0.5],
-// 2^r by a degree-3 minimax polynomial (max rel. error 7.5e-5), exponent patched in with one IMAD per element.
-__device__ __forceinline__ void exp2_poly_pair(float t0, float t1, float& p0, float& p1) {
-  const float kMagic = 12582912.f;  // 1.5 * 2^23
-  t0 = fmaxf(t0, -126.f);
-  t1 = fmaxf(t1, -126.f);
-  const uint64_t t = pack2(t0, t1);
-  const uint64_t xf = fadd2(t, pack2(kMagic, kMagic));
-  const uint64_t n = fadd2(xf, pack2(-kMagic, -kMagic));
-  const uint64_t r = ffma2(n, pack2(-1.f, -1.f), t);
-  uint64_t p = ffma2(pack2(0.05517167f, 0.05517167f), r, pack2(0.24261113f, 0.24261113f));
-  p = ffma2(p, r, pack2(0.69326097f, 0.69326097f));
-  p = ffma2(p, r, pack2(0.99992806f, 0.99992806f));
-  float x0, x1, q0, q1;
-  unpack2(xf, x0, x1);
-  unpack2(p, q0, q1);
-  p0 = __int_as_float(__float_as_int(x0) * (1 << 23) + __float_as_int(q0));
-  p1 = __int_as_float(__float_as_int(x1) * (1 << 23) + __float_as_int(q1));
-}
-
-// One chunk of pass 2: NC S columns (already in registers) -> P (bf16 pairs), returns the chunk's row-sum part.
-template <int NC>
-__device__ __forceinline__ float softmax_chunk(const float* s, uint32_t* pr, float c, float neg_mc) {
-  const uint64_t c2 = pack2(c, c);
-  const uint64_t nm2 = pack2(neg_mc, neg_mc);
-  uint64_t acc = pack2(0.f, 0.f);
-#pragma unroll
-  for (int j = 0; j < NC; j += 2) {
-    float t0, t1, p0, p1;
-    unpack2(ffma2(pack2(s[j], s[j + 1]), c2, nm2), t0, t1);
-    if ((kPolyMask >> ((j >> 1) & 7)) & 1u) {
-      exp2_poly_pair(t0, t1, p0, p1);
-    } else {
-      p0 = ex2_approx(t0);
-      p1 = ex2_approx(t1);
-    }
-    acc = fadd2(acc, pack2(p0, p1));  // row sum uses fp32 P, before bf16 rounding (softmax.h:263-273)
-    pr[j >> 1] = pack_bf16(p0, p1);
-  }
-  float a0, a1;
-  unpack2(acc, a0, a1);
-  return a0 + a1;
-}
-
-// Cold path: write -inf over the S columns >= lim of this thread's TMEM lane (ragged first tile).
-__device__ __noinline__ void mask_ragged_tile(uint32_t s_addr, int lim) {
+// Cold path: write -inf over the S columns >= lim of this thread's TMEM lane (ragged first tile), in TMEM,
+// before the hot path loads S -- so the hot path carries no mask code and no register array escapes.
+__device__ __noinline__ void mask_ragged_tile(uint32_t s_addr, int lim, int ncols) {
 #pragma unroll 1
-  for (int c0 = lim & ~7; c0 < kN; c0 += 8) {
+  for (int c0 = lim & ~7; c0 < ncols; c0 += 8) {
     float v[8];
     if (c0 < lim) {
       tmem_ld_x8(s_addr + c0, reinterpret_cast<uint32_t*>(v));
@@ -162,15 +101,9 @@ __device__ __noinline__ void mask_ragged_tile(uint32_t s_addr, int lim) {
   tmem_wait_st();
 }
 
-template <int NC>
-__device__ __forceinline__ float chunk_max(const float* s, float m) {
-  float m0 = m, m1 = -INFINITY;
-#pragma unroll
-  for (int j = 0; j + 3 < NC; j += 4) {
-    m0 = fmax3(m0, s[j], s[j + 1]);
-    m1 = fmax3(m1, s[j + 2], s[j + 3]);
-  }
-  return fmaxf(m0, m1);
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);  // .x (low 16 bits) = lo
+  return *reinterpret_cast<uint32_t*>(&v);
 }
 
 }  // namespace
@@ -192,8 +125,8 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kOffBar + kNumBars * 8);
   volatile int* num_tiles_smem = reinterpret_cast<volatile int*>(smem + kOffBar + kNumBars * 8 + 4);
-  volatile float* mbox = reinterpret_cast<volatile float*>(smem + kOffMbox);
-  volatile float* fin = reinterpret_cast<volatile float*>(smem + kOffFin);
+  float* xchg = reinterpret_cast<float*>(smem + kOffXchg);
+  float* lx = reinterpret_cast<float*>(smem + kOffLx);
   int* stat_s = reinterpret_cast<int*>(smem + kOffStat);
   uint16_t* seq = reinterpret_cast<uint16_t*>(smem + kOffSeq);
   auto bar = [&](uint32_t idx) { return smem_base + kOffBar + idx * 8; };
@@ -207,10 +140,9 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       mbar_init(bar(kBarVFull + s), 1);
       mbar_init(bar(kBarVEmpty + s), 1);
       mbar_init(bar(kBarSFull + s), 1);
-      mbar_init(bar(kBarPFull + s), 4);  // one arrival per warp of the owning warpgroup
+      mbar_init(bar(kBarPFull + s), kSoftmaxThreads / 32);  // one arrival per softmax warp
     }
     mbar_init(bar(kBarPvDone), 1);
-    mbar_init(bar(kBarOFinal), 1);
     fence_mbar_init();
   }
   if (warp == kProducerWarp) {
@@ -278,12 +210,6 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         const int s = i & 1;
         const int n = seq[i];
         mbar_wait(bar(empty0 + s), ((i >> 1) & 1) ^ 1, 1, i);
-#ifdef LA_EXPERIMENT_NOLOAD   // timing experiment only: reuse the first two tiles' smem, no further TMA traffic
-        if (i >= 2) {
-          mbar_arrive(bar(full0 + s));
-          return;
-        }
-#endif
         mbar_arrive_expect_tx(bar(full0 + s), kKVBytes);
         const uint32_t dst = smem_base + off + s * kKVBytes;
         tma_load_4d(dst, tm, bar(full0 + s), 0, n * kN, head_kv, batch);
@@ -314,26 +240,16 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           umma_ss(d_tmem, q_desc + a_off, k_desc + b_off, kIdescQK, j > 0);
         }
         tc_commit(bar(kBarKEmpty + s));  // K stage reusable once these MMAs retire
-        tc_commit(bar(kBarSFull + s));   // S(i) ready for its softmax warpgroup
+        tc_commit(bar(kBarSFull + s));   // S(i) ready for the softmax warps
       };
-#ifdef LA_PROFILE_CLOCKS
-      long long prof_acc[4] = {0, 0, 0, 0};
-#endif
       mbar_wait(bar(kBarQFull), 0, 3, 0);
       issue_qk(0);
       for (int i = 0; i < T; ++i) {
-        LA_CLK(m0);
         if (i + 1 < T) issue_qk(i + 1);
         const int s = i & 1;
-        LA_CLK(m1);
-        LA_ACC(0, m0, m1);
         mbar_wait(bar(kBarVFull + s), (i >> 1) & 1, 4, i);
-        LA_CLK(m2);
-        LA_ACC(1, m1, m2);
         mbar_wait(bar(kBarPFull + s), (i >> 1) & 1, 5, i);
         tc_fence_after();
-        LA_CLK(m3);
-        LA_ACC(2, m2, m3);
         // V tile is [176 kv rows][64 d] x 2 blocks, i.e. the MN-major B operand:
         //   LBO = distance between the two 64-wide d blocks, SBO = 8 kv rows (1024 B); one k-step = 16 rows.
         const uint64_t v_desc = make_smem_desc_sw128(smem_base + kOffV + s * kKVBytes, kKVBlockBytes, 1024);
@@ -344,90 +260,57 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         }
         tc_commit(bar(kBarVEmpty + s));
         tc_commit(bar(kBarPvDone));
-        LA_CLK(m4);
-        LA_ACC(3, m3, m4);
       }
-      tc_commit(bar(kBarOFinal));
-#ifdef LA_PROFILE_CLOCKS
-      for (int j = 0; j < 4; ++j) atomicAdd(&g_la_prof[8 + j], (unsigned long long)prof_acc[j]);
-#endif
     }
     __syncwarp();
   } else {
-    // ================================================================ softmax warpgroups (2 x 128 threads)
-    const int wg = warp >> 2;                 // 0 = A (even visited tiles, S buffer 0), 1 = B (odd, buffer 1)
-    const int wq = warp & 3;
-    const int row = wq * 32 + lane;           // TMEM lane == query row inside the tile
-    const uint32_t lane_field = (uint32_t)(wq * 32) << 16;
+    // ================================================================ softmax warps (256 threads)
+    const int wg = warp >> 2;                 // column half: 0 -> S[:, 0:88), 1 -> S[:, 88:176)
+    const int row = (warp & 3) * 32 + lane;   // TMEM lane == query row inside the tile
+    const int tid = threadIdx.x;              // 0..255
+    const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
     const float c = args.scale_log2;
     const int q_row = m_block * kM + row;
-    const uint32_t s_addr = tmem_base + kTmemS + wg * kN + lane_field;
-    const uint32_t o_addr = tmem_base + kTmemO + lane_field;
-    const uint32_t bar_recv = 1 + (1 - wg) * 4 + wq;   // the other warpgroup arrives here after publishing its max
-    const uint32_t bar_send = 1 + wg * 4 + wq;
 
-    float m_ref = -INFINITY;  // running max this warpgroup's l is expressed against (raw S units)
-    float l_run = 0.f;        // row sum over this warpgroup's tiles
+    float m_run = -INFINITY;  // true running row max (raw S units)
+    float l_run = 0.f;        // this thread's partial row sum (its 88 columns)
 
-#ifdef LA_PROFILE_CLOCKS
-    long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#endif
-    for (int i = wg; i < T; i += 2) {
+    for (int i = 0; i < T; ++i) {
+      const int buf = i & 1;
       const int n = seq[i];
-      LA_CLK(t0);
-      mbar_wait(bar(kBarSFull + wg), (i >> 1) & 1, 6, i);
+      mbar_wait(bar(kBarSFull + buf), (i >> 1) & 1, 6, i);
       tc_fence_after();
-      LA_CLK(t1);
-      LA_ACC(0, t0, t1);
-#ifdef LA_EXPERIMENT_MMAONLY   // timing experiment only: no softmax work at all, P = whatever is in TMEM
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(kBarPFull + wg));
-      continue;
-#endif
 
-      // The FIRST visited tile is the only one that is seqlen-masked (mask.h:66-76, mainloop :1626): when it is
-      // ragged, -inf is written over its out-of-range S columns in TMEM once (cold, compact loop), so the hot
-      // passes below carry no mask code at all (the fully unrolled masked variants cost more in instruction
-      // fetch stalls than in arithmetic -- ncu: 20-45 % "no instruction" in the softmax passes).
       if (i == 0) {
-        const int lim = args.seqlen_k - n * kN;
-        if (lim < kN) mask_ragged_tile(s_addr, lim);
+        // Key columns >= seqlen_k are masked in the FIRST processed tile only (mask.h:66-76, mainloop :1626).
+        const int lim = args.seqlen_k - (n * kN + wg * kHalfN);
+        if (lim < kHalfN) mask_ragged_tile(tmem_base + kTmemS + wg * kHalfN + lane_field, max(lim, 0), kHalfN);
       }
 
-      // ---------------- pass 1: row max of the tile
-      float m_loc;
-      {
-        float s[64];
-        uint32_t* sr = reinterpret_cast<uint32_t*>(s);
-        tmem_ld_x64(s_addr, sr);
-        tmem_wait_ld();
-        m_loc = chunk_max<64>(s, -INFINITY);
-        tmem_ld_x64(s_addr + 64, sr);
-        tmem_wait_ld();
-        m_loc = chunk_max<64>(s, m_loc);
-        tmem_ld_x32(s_addr + 128, sr);
-        tmem_ld_x16(s_addr + 160, sr + 32);
-        tmem_wait_ld();
-        m_loc = chunk_max<48>(s, m_loc);
-      }
+      float s[kHalfN];
+      uint32_t* sr = reinterpret_cast<uint32_t*>(s);
+      const uint32_t s_addr = tmem_base + kTmemS + buf * kN + wg * kHalfN + lane_field;
+      tmem_ld_x32(s_addr, sr);
+      tmem_ld_x32(s_addr + 32, sr + 32);
+      tmem_ld_x16(s_addr + 64, sr + 64);
+      tmem_ld_x8(s_addr + 80, sr + 80);
+      tmem_wait_ld();
 
-      // ---------------- running max: receive m(i-1) from the other warpgroup, publish m(i)
-      LA_CLK(t2);
-      LA_ACC(1, t1, t2);
-      float m_prev = -INFINITY;
-      if (i > 0) {
-        named_bar_sync(bar_recv, 64);
-        m_prev = mbox[(1 - wg) * kM + row];
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < kHalfN; j += 4) {
+        mx0 = fmax3(mx0, s[j], s[j + 1]);
+        mx1 = fmax3(mx1, s[j + 2], s[j + 3]);
       }
-      LA_CLK(t3);
-      LA_ACC(2, t2, t3);
+      const float m_half = fmaxf(mx0, mx1);
+      // Exchange the half-row maxima between the two warps that own the same 32 rows.
+      xchg[buf * kSoftmaxThreads + tid] = m_half;
+      named_bar_sync(1 + (warp & 3), 64);
+      const float m_loc = fmaxf(m_half, xchg[buf * kSoftmaxThreads + (tid ^ 128)]);
+
+      const float m_prev = m_run;
       const float m_new = fmaxf(m_prev, m_loc);
-      if (i + 1 < T) {
-        mbox[wg * kM + row] = m_new;
-        named_bar_arrive(bar_send, 64);
-      }
-      if (i > 0) {
+      if (wg == 0 && i > 0) {
         // QK-skip statistic: (m_local - m_prev) * scale_log2, reduced with max over the tile's rows.
         const float d = __fmul_rn(__fsub_rn(m_loc, m_prev), c);
         int od = (d != d) ? float_to_ordered(-INFINITY) : float_to_ordered(d);  // NaN compares false upstream
@@ -435,99 +318,76 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         if (lane == 0) atomicMax(&stat_s[i], od);
       }
       const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha_o = ex2_approx((m_prev - m_safe) * c);   // O is expressed against m(i-1)
-      const float alpha_l = ex2_approx((m_ref - m_safe) * c);    // this warpgroup's l against its previous tile
-      m_ref = m_new;
+      const float alpha = ex2_approx((m_prev - m_safe) * c);
+      m_run = m_new;
       const float neg_mc = -m_safe * c;
 
-      // ---------------- pass 2: P = exp2(S*c - m*c), row sum, bf16 P written over the S buffer
-      // Five chunks of 32 S columns + one of 16; P chunk k (16 columns of bf16 pairs) lands on columns
-      // [16k, 16k+16) -- always behind the S columns [32k, 32k+32) still to be read, and only this thread
-      // touches this TMEM lane.  Two register buffers: the next chunk's tcgen05.ld is in flight while the
-      // current one is exponentiated.  The loop is kept rolled (two chunk bodies + tail) to stay inside the
-      // instruction cache; 32-wide chunks keep the per-chunk MUFU-latency drain to six per tile.
-      float lsum = 0.f;
-      {
-        float sa[32], sb[32];
-        uint32_t pr[16];
-        tmem_ld_x32(s_addr, reinterpret_cast<uint32_t*>(sa));
-        tmem_wait_ld();
-#pragma unroll 1
-        for (int k = 0; k < 4; k += 2) {
-          tmem_ld_x32(s_addr + 32 * (k + 1), reinterpret_cast<uint32_t*>(sb));
-          lsum += softmax_chunk<32>(sa, pr, c, neg_mc);
-          tmem_st_x16(s_addr + 16 * k, pr);
-          tmem_wait_ld();
-          tmem_ld_x32(s_addr + 32 * (k + 2), reinterpret_cast<uint32_t*>(sa));
-          lsum += softmax_chunk<32>(sb, pr, c, neg_mc);
-          tmem_st_x16(s_addr + 16 * (k + 1), pr);
-          tmem_wait_ld();
-        }
-        // sa = chunk 4 (columns 128..159); the 16-column tail goes through sb
-        tmem_ld_x16(s_addr + 160, reinterpret_cast<uint32_t*>(sb));
-        lsum += softmax_chunk<32>(sa, pr, c, neg_mc);
-        tmem_st_x16(s_addr + 64, pr);
-        tmem_wait_ld();
-        lsum += softmax_chunk<16>(sb, pr, c, neg_mc);
-        tmem_st_x8(s_addr + 80, pr);
+      uint32_t pr[kHalfN / 2];
+      const uint64_t c2 = pack2(c, c);
+      const uint64_t nm2 = pack2(neg_mc, neg_mc);
+      uint64_t acc0 = pack2(0.f, 0.f), acc1 = pack2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < kHalfN; j += 4) {
+        float t0, t1, t2, t3;
+        unpack2(ffma2(pack2(s[j], s[j + 1]), c2, nm2), t0, t1);
+        unpack2(ffma2(pack2(s[j + 2], s[j + 3]), c2, nm2), t2, t3);
+        const float p0 = ex2_approx(t0), p1 = ex2_approx(t1), p2 = ex2_approx(t2), p3 = ex2_approx(t3);
+        acc0 = fadd2(acc0, pack2(p0, p1));   // row sum uses fp32 P, before bf16 rounding (softmax.h:263-273)
+        acc1 = fadd2(acc1, pack2(p2, p3));
+        pr[j / 2] = pack_bf16(p0, p1);
+        pr[j / 2 + 1] = pack_bf16(p2, p3);
       }
-      l_run = l_run * alpha_l + lsum;
-      LA_CLK(t4);
-      LA_ACC(3, t3, t4);
+      float a0, a1, a2, a3;
+      unpack2(acc0, a0, a1);
+      unpack2(acc1, a2, a3);
+      l_run = l_run * alpha + ((a0 + a1) + (a2 + a3));
 
       if (i > 0) {
         // O may only be touched between PV(i-1) retiring and PV(i) being issued.
         mbar_wait(bar(kBarPvDone), (i - 1) & 1, 7, i);
         tc_fence_after();
-        if (__any_sync(0xffffffffu, alpha_o != 1.0f)) {
-#pragma unroll 1
-          for (int h = 0; h < 4; ++h) {
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+          const uint32_t o_addr = tmem_base + kTmemO + wg * 64 + lane_field;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
             float o[32];
             tmem_ld_x32(o_addr + h * 32, reinterpret_cast<uint32_t*>(o));
             tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] *= alpha_o;
+            for (int j = 0; j < 32; ++j) o[j] *= alpha;
             tmem_st_x32(o_addr + h * 32, reinterpret_cast<uint32_t*>(o));
           }
         }
       }
-      LA_CLK(t5);
-      LA_ACC(4, t4, t5);
+      // P (bf16 pairs) goes over the first 88 columns of this S buffer: wg0 -> [0,44), wg1 -> [44,88).
+      // Safe: both half-row owners finished reading S before the named barrier above.
+      const uint32_t p_addr = tmem_base + kTmemS + buf * kN + wg * (kHalfN / 2) + lane_field;
+      tmem_st_x32(p_addr, pr);
+      tmem_st_x8(p_addr + 32, pr + 32);
+      tmem_st_x4(p_addr + 40, pr + 40);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(kBarPFull + wg));
-      LA_CLK(t6);
-      LA_ACC(5, t5, t6);
+      if (lane == 0) mbar_arrive(bar(kBarPFull + buf));
     }
-#ifdef LA_PROFILE_CLOCKS
-    if (lane == 0 && wq == 0) {
-      for (int j = 0; j < 6; ++j) atomicAdd(&g_la_prof[j], (unsigned long long)prof_acc[j]);
-      if (wg == 0) atomicAdd(&g_la_prof[15], (unsigned long long)T);
-    }
-#endif
 
-    // ---------------- epilogue: merge the two warpgroups' (l, m_ref), normalise, store
-    fin[(wg * 2 + 0) * kM + row] = l_run;
-    fin[(wg * 2 + 1) * kM + row] = m_ref;
-    named_bar_sync(9 + wq, 64);
+    // ---------------------------------------------------------------- epilogue
     float inv = 0.f, lse = -INFINITY;
     if (T > 0) {
-      const float l_o = fin[((1 - wg) * 2 + 0) * kM + row];
-      const float m_o = fin[((1 - wg) * 2 + 1) * kM + row];
-      const float m_fin = fmaxf(m_ref, m_o);                      // the running max is monotone
-      const float m_fs = (m_fin == -INFINITY) ? 0.f : m_fin;
-      const float l_tot = l_run * ex2_approx((m_ref - m_fs) * c) + l_o * ex2_approx((m_o - m_fs) * c);
+      lx[tid] = l_run;
+      named_bar_sync(1 + (warp & 3), 64);
+      const float l_tot = l_run + lx[tid ^ 128];
       const bool bad = (l_tot == 0.f) || (l_tot != l_tot);
-      inv = bad ? 0.f : 1.0f / l_tot;                             // softmax.h:283-293
-      lse = bad ? -INFINITY : m_fin * args.softmax_scale + logf(l_tot);
-      mbar_wait(bar(kBarOFinal), 0, 8, T);
+      inv = bad ? 0.f : 1.0f / l_tot;                                              // softmax.h:283-293
+      lse = bad ? -INFINITY : m_run * args.softmax_scale + logf(l_tot);
+      mbar_wait(bar(kBarPvDone), (T - 1) & 1, 8, T);
       tc_fence_after();
     }
-    // warpgroup A stores O[:, 0:64), B stores O[:, 64:128)
     float o[64];
     if (T > 0) {
-      tmem_ld_x64(o_addr + wg * 64, reinterpret_cast<uint32_t*>(o));
+      const uint32_t o_addr = tmem_base + kTmemO + wg * 64 + lane_field;
+      tmem_ld_x32(o_addr, reinterpret_cast<uint32_t*>(o));
+      tmem_ld_x32(o_addr + 32, reinterpret_cast<uint32_t*>(o) + 32);
       tmem_wait_ld();
     } else {
 #pragma unroll

@@ -211,6 +211,20 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return d;
 }
 
+// ---- explicit shared-space accesses (a generic pointer derived from the aligned dynamic-smem base makes nvcc emit
+// generic LD/ST/ATOM; these keep the hot loop on LDS/STS/ATOMS) ------------------------------------------
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_smax_s32(uint32_t addr, int v) {
+  asm volatile("red.shared.max.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 // order-preserving float -> int map (NaN must be filtered by the caller)
 __device__ __forceinline__ int float_to_ordered(float f) {
   int i = __float_as_int(f);

@@ -7,7 +7,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libliteattn_b200.so")
+# LITEATTN_B200_LIB: developer override used by tools/ to time experimental builds of the same ABI.
+LIB_PATH = os.environ.get("LITEATTN_B200_LIB") or os.path.join(_HERE, "libliteattn_b200.so")
 
 BLOCK_M = 128
 BLOCK_N = 176

@@ -28,18 +28,20 @@ def up_to_date():
     return all(os.path.getmtime(os.path.join(HERE, d)) <= t for d in DEPS)
 
 
-def build(verbose=False, force=False):
-    if not force and up_to_date():
+def build(verbose=False, force=False, out=None, defines=()):
+    """out/defines: experimental variants (tools/build_variants.py); the product build uses neither."""
+    if out is None and not force and up_to_date():
         return OUT
+    out = out or OUT
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-           "-Xptxas", "-v", "--shared", "-Xcompiler", "-fPIC",
-           "-o", OUT] + [os.path.join(HERE, s) for s in SOURCES]
+           "-Xptxas", "-v", "--shared", "-Xcompiler", "-fPIC"] + [f"-D{d}" for d in defines] + [
+           "-o", out] + [os.path.join(HERE, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libliteattn_b200.so")
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

@@ -69,8 +69,9 @@ enum Bar : uint32_t {
   kBarVEmpty = 7,
   kBarSFull = 9,   // +buf
   kBarPFull = 11,  // +buf
-  kBarPvDone = 13,
-  kNumBars = 14
+  kBarPvDone = 13,  // one arrival per PV: waited on (phase i-1) only by tiles that rescale O
+  kBarOFull = 14,   // the last PV retired: O is final
+  kNumBars = 15
 };
 
 constexpr uint32_t kTmemCols = 512;
@@ -104,6 +105,127 @@ __device__ __noinline__ void mask_ragged_tile(uint32_t s_addr, int lim, int ncol
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);  // .x (low 16 bits) = lo
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// exp2 on the FMA pipe for these column pairs of every 8 (bit p set => pair p of the group uses the polynomial).
+// MUFU.EX2 runs at 16/clk/SM: 128x176 exponentials take exactly as long as the tile's two MMAs (1408 clk), so a
+// share of them has to come off the MUFU pipe for the softmax to fit under the tensor pipe at all.
+#ifndef LA_POLY_MASK
+#define LA_POLY_MASK 0x00u   // measured on B200 (S=32768,H=16 sustained): 0/8 1077, 1/8 1041, 2/8 1005, 3/8 986 TFLOP/s
+#endif
+constexpr uint32_t kPolyMask = LA_POLY_MASK;
+
+// The scaling reference m_ref of a row trails its true running max by at most kLazyTau (log2 units): P <= 2^tau.
+// While the true max stays within tau of m_ref, P(i) does not depend on tile i's own max, so the exponentials
+// start as soon as S arrives and O never needs rescaling.  (The QK-skip statistic always uses the TRUE max.)
+#ifndef LA_LAZY_TAU
+#define LA_LAZY_TAU 8.0f
+#endif
+constexpr float kLazyTau = LA_LAZY_TAU;
+
+// 2^t for a pair on the FMA pipe: n = round(t) via the 1.5*2^23 trick, r = t - n in [-0.5, 0.5], 2^r by a
+// degree-3 minimax polynomial (max rel. error 7.5e-5, below bf16 rounding of P), exponent patched in with one
+// integer multiply-add per element.
+__device__ __forceinline__ void exp2_poly_pair(float t0, float t1, float& p0, float& p1) {
+  const float kMagic = 12582912.f;  // 1.5 * 2^23
+  t0 = fmaxf(t0, -126.f);
+  t1 = fmaxf(t1, -126.f);
+  const uint64_t t = pack2(t0, t1);
+  const uint64_t xf = fadd2(t, pack2(kMagic, kMagic));
+  const uint64_t n = fadd2(xf, pack2(-kMagic, -kMagic));
+  const uint64_t r = ffma2(n, pack2(-1.f, -1.f), t);
+  uint64_t p = ffma2(pack2(0.05517167f, 0.05517167f), r, pack2(0.24261113f, 0.24261113f));
+  p = ffma2(p, r, pack2(0.69326097f, 0.69326097f));
+  p = ffma2(p, r, pack2(0.99992806f, 0.99992806f));
+  float x0, x1, q0, q1;
+  unpack2(xf, x0, x1);
+  unpack2(p, q0, q1);
+  p0 = __int_as_float(__float_as_int(x0) * (1 << 23) + __float_as_int(q0));
+  p1 = __int_as_float(__float_as_int(x1) * (1 << 23) + __float_as_int(q1));
+}
+
+struct SlowTileArgs {
+  uint32_t s_addr;      // this thread's half of S (TMEM, lane field included)
+  uint32_t p_addr;      // where this thread's 44 bf16x2 P columns go
+  uint32_t o_addr;      // this thread's 64 O columns
+  uint32_t xchg_mine, xchg_other;  // smem byte addresses of the half-row max exchange slots
+  uint32_t bar_id;      // named barrier of the warp pair owning these 32 rows
+  uint32_t bar_pv_done; // mbarrier: PV(i-1) retired
+  int i;                // visit index of the tile
+  int mask_lim;         // < kHalfN: columns >= mask_lim of this half are out of range (first tile only)
+  float c;
+  float m_loc;          // in: full-row max of this tile if known (have_mloc); out: always
+  int have_mloc;
+  float m_true;         // in: true running max before this tile
+  float m_ref;          // in/out: scaling reference
+  float l_run;          // in/out: partial row sum (this thread's columns), relative to m_ref
+};
+
+// The exact (non-speculative) tile: first visited tile of every CTA, and any tile whose row max runs more than
+// kLazyTau ahead of the reference.  m_ref := true running max, l and O are rescaled, P is recomputed from S
+// (still intact in TMEM) entirely on MUFU.  Out of line: it runs for ~0.5 % of the tiles.
+__device__ __noinline__ void softmax_slow_tile(SlowTileArgs* a) {
+  const float c = a->c;
+  if (a->mask_lim < kHalfN) mask_ragged_tile(a->s_addr, max(a->mask_lim, 0), kHalfN);
+  float s[kHalfN];
+  uint32_t* sr = reinterpret_cast<uint32_t*>(s);
+  tmem_ld_x32(a->s_addr, sr);
+  tmem_ld_x32(a->s_addr + 32, sr + 32);
+  tmem_ld_x16(a->s_addr + 64, sr + 64);
+  tmem_ld_x8(a->s_addr + 80, sr + 80);
+  tmem_wait_ld();
+  float m_loc = a->m_loc;
+  if (!a->have_mloc) {
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kHalfN; j += 4) {
+      mx0 = fmax3(mx0, s[j], s[j + 1]);
+      mx1 = fmax3(mx1, s[j + 2], s[j + 3]);
+    }
+    const float m_half = fmaxf(mx0, mx1);
+    sts_f32(a->xchg_mine, m_half);
+    named_bar_sync(a->bar_id, 64);
+    m_loc = fmaxf(m_half, lds_f32(a->xchg_other));
+    a->m_loc = m_loc;
+  } else {
+    // The partner warp's P lands on S columns this warp has just re-read: order its store after our load.
+    named_bar_sync(a->bar_id, 64);
+  }
+  const float m_new = fmaxf(a->m_true, m_loc);
+  const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
+  const float alpha = ex2_approx((a->m_ref - m_safe) * c);   // m_ref = -inf before the first tile -> 0
+  a->m_ref = m_safe;
+  const float neg_mc = -m_safe * c;
+  uint32_t pr[kHalfN / 2];
+  float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < kHalfN; j += 2) {
+    const float p0 = ex2_approx(fmaf(s[j], c, neg_mc)), p1 = ex2_approx(fmaf(s[j + 1], c, neg_mc));
+    sum0 += p0;
+    sum1 += p1;
+    pr[j / 2] = pack_bf16(p0, p1);
+  }
+  a->l_run = a->l_run * alpha + (sum0 + sum1);
+  if (a->i > 0) {
+    // O may only be touched between PV(i-1) retiring and PV(i) being issued.
+    mbar_wait(a->bar_pv_done, (a->i - 1) & 1, 7, a->i);
+    tc_fence_after();
+    if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll 1
+      for (int h = 0; h < 4; ++h) {
+        float o[16];
+        tmem_ld_x16(a->o_addr + h * 16, reinterpret_cast<uint32_t*>(o));
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] *= alpha;
+        tmem_st_x16(a->o_addr + h * 16, reinterpret_cast<uint32_t*>(o));
+      }
+    }
+  }
+  tmem_st_x32(a->p_addr, pr);
+  tmem_st_x8(a->p_addr + 32, pr + 32);
+  tmem_st_x4(a->p_addr + 40, pr + 40);
+  tmem_wait_st();
 }
 
 }  // namespace
@@ -143,6 +265,7 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       mbar_init(bar(kBarPFull + s), kSoftmaxThreads / 32);  // one arrival per softmax warp
     }
     mbar_init(bar(kBarPvDone), 1);
+    mbar_init(bar(kBarOFull), 1);
     fence_mbar_init();
   }
   if (warp == kProducerWarp) {
@@ -260,6 +383,9 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         }
         tc_commit(bar(kBarVEmpty + s));
         tc_commit(bar(kBarPvDone));
+        // Not kBarPvDone: a parity wait is only meaningful one phase behind, and the speculative tiles never
+        // wait on it, so by the epilogue that barrier may be two phases ahead of a warp's last wait.
+        if (i == T - 1) tc_commit(bar(kBarOFull));
       }
     }
     __syncwarp();
@@ -272,103 +398,122 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     const float c = args.scale_log2;
     const int q_row = m_block * kM + row;
 
-    float m_run = -INFINITY;  // true running row max (raw S units)
-    float l_run = 0.f;        // this thread's partial row sum (its 88 columns)
+    float m_true = -INFINITY;  // true running row max (raw S units): the QK-skip statistic is defined on it
+    float m_ref = -INFINITY;   // scaling reference: P = 2^((S - m_ref) c); m_true - m_ref <= kLazyTau / c
+    float l_run = 0.f;         // this thread's partial row sum (its 88 columns), relative to m_ref
+
+    const uint32_t xchg_base = smem_base + kOffXchg;
+    const uint32_t stat_base = smem_base + kOffStat;
+    const uint32_t pair_bar = 1 + (warp & 3);
+    const uint64_t c2 = pack2(c, c);
 
     for (int i = 0; i < T; ++i) {
       const int buf = i & 1;
-      const int n = seq[i];
       mbar_wait(bar(kBarSFull + buf), (i >> 1) & 1, 6, i);
       tc_fence_after();
 
-      if (i == 0) {
-        // Key columns >= seqlen_k are masked in the FIRST processed tile only (mask.h:66-76, mainloop :1626).
-        const int lim = args.seqlen_k - (n * kN + wg * kHalfN);
-        if (lim < kHalfN) mask_ragged_tile(tmem_base + kTmemS + wg * kHalfN + lane_field, max(lim, 0), kHalfN);
-      }
-
-      float s[kHalfN];
-      uint32_t* sr = reinterpret_cast<uint32_t*>(s);
       const uint32_t s_addr = tmem_base + kTmemS + buf * kN + wg * kHalfN + lane_field;
-      tmem_ld_x32(s_addr, sr);
-      tmem_ld_x32(s_addr + 32, sr + 32);
-      tmem_ld_x16(s_addr + 64, sr + 64);
-      tmem_ld_x8(s_addr + 80, sr + 80);
-      tmem_wait_ld();
+      // P (bf16 pairs) goes over the first 88 columns of this S buffer: wg0 -> [0,44), wg1 -> [44,88).
+      // Safe: it is stored only after both half-row owners have read S (named barrier below).
+      const uint32_t p_addr = tmem_base + kTmemS + buf * kN + wg * (kHalfN / 2) + lane_field;
+      const uint32_t xchg_mine = xchg_base + (buf * kSoftmaxThreads + tid) * 4;
+      const uint32_t xchg_other = xchg_base + (buf * kSoftmaxThreads + (tid ^ 128)) * 4;
 
-      float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < kHalfN; j += 4) {
-        mx0 = fmax3(mx0, s[j], s[j + 1]);
-        mx1 = fmax3(mx1, s[j + 2], s[j + 3]);
-      }
-      const float m_half = fmaxf(mx0, mx1);
-      // Exchange the half-row maxima between the two warps that own the same 32 rows.
-      xchg[buf * kSoftmaxThreads + tid] = m_half;
-      named_bar_sync(1 + (warp & 3), 64);
-      const float m_loc = fmaxf(m_half, xchg[buf * kSoftmaxThreads + (tid ^ 128)]);
+      float m_loc;
+      bool slow = (i == 0);
+      if (!slow) {
+        // ---------------- speculative tile: exponentials against the current reference, row max on the side
+        float s[kHalfN];
+        uint32_t* sr = reinterpret_cast<uint32_t*>(s);
+        tmem_ld_x32(s_addr, sr);
+        tmem_ld_x32(s_addr + 32, sr + 32);
+        tmem_ld_x16(s_addr + 64, sr + 64);
+        tmem_ld_x8(s_addr + 80, sr + 80);
+        tmem_wait_ld();
 
-      const float m_prev = m_run;
-      const float m_new = fmaxf(m_prev, m_loc);
-      if (wg == 0 && i > 0) {
-        // QK-skip statistic: (m_local - m_prev) * scale_log2, reduced with max over the tile's rows.
-        const float d = __fmul_rn(__fsub_rn(m_loc, m_prev), c);
-        int od = (d != d) ? float_to_ordered(-INFINITY) : float_to_ordered(d);  // NaN compares false upstream
-        od = __reduce_max_sync(0xffffffffu, od);
-        if (lane == 0) atomicMax(&stat_s[i], od);
-      }
-      const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = ex2_approx((m_prev - m_safe) * c);
-      m_run = m_new;
-      const float neg_mc = -m_safe * c;
-
-      uint32_t pr[kHalfN / 2];
-      const uint64_t c2 = pack2(c, c);
-      const uint64_t nm2 = pack2(neg_mc, neg_mc);
-      uint64_t acc0 = pack2(0.f, 0.f), acc1 = pack2(0.f, 0.f);
+        const float neg_mc = -m_ref * c;
+        const uint64_t nm2 = pack2(neg_mc, neg_mc);
+        uint32_t pr[kHalfN / 2];
+        uint64_t acc0 = pack2(0.f, 0.f), acc1 = pack2(0.f, 0.f);
+        float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < kHalfN; j += 4) {
-        float t0, t1, t2, t3;
-        unpack2(ffma2(pack2(s[j], s[j + 1]), c2, nm2), t0, t1);
-        unpack2(ffma2(pack2(s[j + 2], s[j + 3]), c2, nm2), t2, t3);
-        const float p0 = ex2_approx(t0), p1 = ex2_approx(t1), p2 = ex2_approx(t2), p3 = ex2_approx(t3);
-        acc0 = fadd2(acc0, pack2(p0, p1));   // row sum uses fp32 P, before bf16 rounding (softmax.h:263-273)
-        acc1 = fadd2(acc1, pack2(p2, p3));
-        pr[j / 2] = pack_bf16(p0, p1);
-        pr[j / 2 + 1] = pack_bf16(p2, p3);
-      }
-      float a0, a1, a2, a3;
-      unpack2(acc0, a0, a1);
-      unpack2(acc1, a2, a3);
-      l_run = l_run * alpha + ((a0 + a1) + (a2 + a3));
-
-      if (i > 0) {
-        // O may only be touched between PV(i-1) retiring and PV(i) being issued.
-        mbar_wait(bar(kBarPvDone), (i - 1) & 1, 7, i);
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
-          const uint32_t o_addr = tmem_base + kTmemO + wg * 64 + lane_field;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            float o[32];
-            tmem_ld_x32(o_addr + h * 32, reinterpret_cast<uint32_t*>(o));
-            tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] *= alpha;
-            tmem_st_x32(o_addr + h * 32, reinterpret_cast<uint32_t*>(o));
+        for (int j = 0; j < kHalfN; j += 4) {
+          mx0 = fmax3(mx0, s[j], s[j + 1]);
+          mx1 = fmax3(mx1, s[j + 2], s[j + 3]);
+          float t0, t1, t2, t3, p0, p1, p2, p3;
+          unpack2(ffma2(pack2(s[j], s[j + 1]), c2, nm2), t0, t1);
+          unpack2(ffma2(pack2(s[j + 2], s[j + 3]), c2, nm2), t2, t3);
+          if ((kPolyMask >> ((j >> 1) & 7)) & 1u) {
+            exp2_poly_pair(t0, t1, p0, p1);
+          } else {
+            p0 = ex2_approx(t0);
+            p1 = ex2_approx(t1);
           }
+          if ((kPolyMask >> (((j >> 1) + 1) & 7)) & 1u) {
+            exp2_poly_pair(t2, t3, p2, p3);
+          } else {
+            p2 = ex2_approx(t2);
+            p3 = ex2_approx(t3);
+          }
+          acc0 = fadd2(acc0, pack2(p0, p1));   // row sum uses fp32 P, before bf16 rounding (softmax.h:263-273)
+          acc1 = fadd2(acc1, pack2(p2, p3));
+          pr[j / 2] = pack_bf16(p0, p1);
+          pr[j / 2 + 1] = pack_bf16(p2, p3);
+        }
+        const float m_half = fmaxf(mx0, mx1);
+        // Exchange the half-row maxima between the two warps that own the same 32 rows.
+        sts_f32(xchg_mine, m_half);
+        named_bar_sync(pair_bar, 64);
+        m_loc = fmaxf(m_half, lds_f32(xchg_other));
+        // Both warps of the pair see the same m_loc and m_ref for the same rows => the same verdict.
+        slow = __any_sync(0xffffffffu, !((m_loc - m_ref) * c <= kLazyTau));
+        if (!slow) {
+          float a0, a1, a2, a3;
+          unpack2(acc0, a0, a1);
+          unpack2(acc1, a2, a3);
+          l_run += (a0 + a1) + (a2 + a3);
+          tmem_st_x32(p_addr, pr);
+          tmem_st_x8(p_addr + 32, pr + 32);
+          tmem_st_x4(p_addr + 40, pr + 40);
+          tmem_wait_st();
         }
       }
-      // P (bf16 pairs) goes over the first 88 columns of this S buffer: wg0 -> [0,44), wg1 -> [44,88).
-      // Safe: both half-row owners finished reading S before the named barrier above.
-      const uint32_t p_addr = tmem_base + kTmemS + buf * kN + wg * (kHalfN / 2) + lane_field;
-      tmem_st_x32(p_addr, pr);
-      tmem_st_x8(p_addr + 32, pr + 32);
-      tmem_st_x4(p_addr + 40, pr + 40);
-      tmem_wait_st();
+      if (slow) {
+        SlowTileArgs a;
+        a.s_addr = s_addr;
+        a.p_addr = p_addr;
+        a.o_addr = tmem_base + kTmemO + wg * 64 + lane_field;
+        a.xchg_mine = xchg_mine;
+        a.xchg_other = xchg_other;
+        a.bar_id = pair_bar;
+        a.bar_pv_done = bar(kBarPvDone);
+        a.i = i;
+        // Key columns >= seqlen_k are masked in the FIRST processed tile only (mask.h:66-76, mainloop :1626).
+        a.mask_lim = (i == 0) ? args.seqlen_k - (seq[0] * kN + wg * kHalfN) : kHalfN;
+        a.c = c;
+        a.m_loc = m_loc;
+        a.have_mloc = (i != 0);
+        a.m_true = m_true;
+        a.m_ref = m_ref;
+        a.l_run = l_run;
+        softmax_slow_tile(&a);
+        m_loc = a.m_loc;
+        m_ref = a.m_ref;
+        l_run = a.l_run;
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(kBarPFull + buf));
+
+      // ---------------- off the critical path: QK-skip statistic and the true running max
+      if (wg == 0 && i > 0) {
+        // (m_local - m_prev) * scale_log2 (softmax.h:194), reduced with max over the tile's 128 rows.
+        const float d = __fmul_rn(__fsub_rn(m_loc, m_true), c);
+        int od = (d != d) ? float_to_ordered(-INFINITY) : float_to_ordered(d);  // NaN compares false upstream
+        od = __reduce_max_sync(0xffffffffu, od);
+        if (lane == 0) red_smax_s32(stat_base + i * 4, od);
+      }
+      m_true = fmaxf(m_true, m_loc);
     }
 
     // ---------------------------------------------------------------- epilogue
@@ -379,8 +524,8 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       const float l_tot = l_run + lx[tid ^ 128];
       const bool bad = (l_tot == 0.f) || (l_tot != l_tot);
       inv = bad ? 0.f : 1.0f / l_tot;                                              // softmax.h:283-293
-      lse = bad ? -INFINITY : m_run * args.softmax_scale + logf(l_tot);
-      mbar_wait(bar(kBarPvDone), (T - 1) & 1, 8, T);
+      lse = bad ? -INFINITY : m_ref * args.softmax_scale + logf(l_tot);
+      mbar_wait(bar(kBarOFull), 0, 8, T);
       tc_fence_after();
     }
     float o[64];

@@ -104,6 +104,17 @@ int la_get_tile_mn(int head_dim, int element_size, int v_colmajor, int* block_m,
   return (element_size == 2 && head_dim == LA_HEAD_DIM) ? LA_OK : LA_ERR_UNSUPPORTED;
 }
 
+#ifdef LA_PROFILE_CLOCKS
+int la_prof_read(unsigned long long out[32], int reset) {
+  LA_CUDA(cudaMemcpyFromSymbol(out, la::g_la_prof, 32 * sizeof(unsigned long long)));
+  if (reset) {
+    unsigned long long z[32] = {0};
+    LA_CUDA(cudaMemcpyToSymbol(la::g_la_prof, z, sizeof(z)));
+  }
+  return LA_OK;
+}
+#endif
+
 int la_watchdog_read(unsigned int out[4]) {
   LA_CUDA(cudaMemcpyFromSymbol(out, la::g_la_watchdog, 4 * sizeof(unsigned int)));
   return LA_OK;

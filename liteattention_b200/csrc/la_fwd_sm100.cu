@@ -34,6 +34,21 @@
 
 namespace la {
 
+// Developer-only cycle accounting (tools/prof_clocks.py builds a variant with -DLA_PROFILE_CLOCKS): clock64 deltas
+// of the role leaders summed per phase.  Compiled out of the product build.
+#ifdef LA_PROFILE_CLOCKS
+__device__ unsigned long long g_la_prof[32];
+#define LA_CLK(var) const long long var = clock64()
+#define LA_ACC(idx, a, b) prof_acc[idx] += (b) - (a)
+#define LA_PROF_DECL(n) long long prof_acc[n] = {}
+#define LA_PROF_FLUSH(base, n) for (int j_ = 0; j_ < (n); ++j_) atomicAdd(&g_la_prof[(base) + j_], (unsigned long long)prof_acc[j_])
+#else
+#define LA_CLK(var)
+#define LA_ACC(idx, a, b)
+#define LA_PROF_DECL(n)
+#define LA_PROF_FLUSH(base, n)
+#endif
+
 namespace {
 
 constexpr int kM = 128;        // query rows per CTA
@@ -43,6 +58,8 @@ constexpr int kHalfN = kN / 2; // S columns per softmax warpgroup
 constexpr int kSoftmaxThreads = 256;
 constexpr int kProducerWarp = 8;
 constexpr int kMmaWarp = 9;
+constexpr int kRegsSoftmax = 216;   // 8 warps x 32 x 216 + 4 warps x 32 x 72 = 64512 = the 12 x 32 x 168 the CTA launches with
+constexpr int kRegsOther = 72;
 
 constexpr uint32_t kQBlockBytes = kM * 128;   // one 64-column (128 B) swizzled block of Q
 constexpr uint32_t kKVBlockBytes = kN * 128;  // one 64-column block of a K or V tile (22528 = 22 * 1024)
@@ -149,7 +166,7 @@ struct SlowTileArgs {
   uint32_t p_addr;      // where this thread's 44 bf16x2 P columns go
   uint32_t o_addr;      // this thread's 64 O columns
   uint32_t xchg_mine, xchg_other;  // smem byte addresses of the half-row max exchange slots
-  uint32_t bar_id;      // named barrier of the warp pair owning these 32 rows
+  uint32_t bar_tx, bar_rx;  // split named barriers of the warp pair owning these 32 rows (arrive on tx, sync on rx)
   uint32_t bar_pv_done; // mbarrier: PV(i-1) retired
   int i;                // visit index of the tile
   int mask_lim;         // < kHalfN: columns >= mask_lim of this half are out of range (first tile only)
@@ -184,12 +201,14 @@ __device__ __noinline__ void softmax_slow_tile(SlowTileArgs* a) {
     }
     const float m_half = fmaxf(mx0, mx1);
     sts_f32(a->xchg_mine, m_half);
-    named_bar_sync(a->bar_id, 64);
+    named_bar_arrive(a->bar_tx, 64);
+    named_bar_sync(a->bar_rx, 64);
     m_loc = fmaxf(m_half, lds_f32(a->xchg_other));
     a->m_loc = m_loc;
   } else {
     // The partner warp's P lands on S columns this warp has just re-read: order its store after our load.
-    named_bar_sync(a->bar_id, 64);
+    named_bar_arrive(a->bar_tx, 64);
+    named_bar_sync(a->bar_rx, 64);
   }
   const float m_new = fmaxf(a->m_true, m_loc);
   const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
@@ -322,6 +341,11 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
   const uint32_t tmem_base = *tmem_ptr_smem;
   const int T = *num_tiles_smem;
 
+  // 12 warps x 168 registers at launch; the softmax threads need ~200 (88 S values prefetched for the next tile
+  // while 44 packed P registers of the current one are still live), the producer / issuer warps almost none.
+  // setmaxnreg is a warpgroup-wide instruction: all four warps of a group must run the SAME instance of it.
+  if (warp >= 8) {
+  setmaxnreg_dec<kRegsOther>();   // warps 10-11 only complete this warpgroup
   if (warp == kProducerWarp) {
     // ================================================================ TMA producer (one lane)
     if (lane == 0 && T > 0) {
@@ -329,10 +353,20 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       tma_load_4d(smem_base + kOffQ, &tmap_q, bar(kBarQFull), 0, m_block * kM, head, batch);
       tma_load_4d(smem_base + kOffQ + kQBlockBytes, &tmap_q, bar(kBarQFull), 64, m_block * kM, head, batch);
 
+      LA_PROF_DECL(2);
       auto load_kv = [&](const CUtensorMap* tm, uint32_t off, uint32_t full0, uint32_t empty0, int i) {
         const int s = i & 1;
         const int n = seq[i];
+        LA_CLK(p0);
         mbar_wait(bar(empty0 + s), ((i >> 1) & 1) ^ 1, 1, i);
+        LA_CLK(p1);
+        LA_ACC(empty0 == kBarKEmpty ? 0 : 1, p0, p1);
+#ifdef LA_EXPERIMENT_NOLOAD   // timing experiment only (wrong results): reuse the first two tiles' smem, no further TMA traffic
+        if (i >= 2) {
+          mbar_arrive(bar(full0 + s));
+          return;
+        }
+#endif
         mbar_arrive_expect_tx(bar(full0 + s), kKVBytes);
         const uint32_t dst = smem_base + off + s * kKVBytes;
         tma_load_4d(dst, tm, bar(full0 + s), 0, n * kN, head_kv, batch);
@@ -343,54 +377,92 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         if (i + 1 < T) load_kv(&tmap_k, kOffK, kBarKFull, kBarKEmpty, i + 1);
         load_kv(&tmap_v, kOffV, kBarVFull, kBarVEmpty, i);
       }
+      LA_PROF_FLUSH(16, 2);
     }
     __syncwarp();
   } else if (warp == kMmaWarp) {
-    // ================================================================ tcgen05 issuer (one lane)
-    if (lane == 0 && T > 0) {
-      const uint64_t q_desc = make_smem_desc_sw128(smem_base + kOffQ, 16, 1024);
-      auto issue_qk = [&](int i) {
-        const int s = i & 1;
+    // ================================================================ tcgen05 issuer
+    // The whole warp walks the loop converged and one elected lane issues: with warp-uniform control flow the
+    // descriptors live in uniform registers.  (Issuing from inside `if (lane == 0)` made ptxas rebuild every
+    // operand with ELECT + 4-6 dependent R2UR per MMA, ~80 clk of issue latency per instruction -- more than the
+    // MMA itself takes to execute -- and the tensor pipe starved: tools/prof_clocks.py.)
+    const int Tu = __reduce_max_sync(0xffffffffu, T);   // same value in every lane; tells nvcc it is uniform
+    if (Tu > 0) {
+      const uint32_t q_lo = ((smem_base + kOffQ) >> 4) & 0x3FFFu;
+      const uint32_t k_lo = ((smem_base + kOffK) >> 4) & 0x3FFFu;
+      const uint32_t v_lo = ((smem_base + kOffV) >> 4) & 0x3FFFu;
+      constexpr uint64_t kDescKMajorHi = make_smem_desc_sw128(0, 16, 1024);            // Q and K: K-major
+      constexpr uint64_t kDescVHi = make_smem_desc_sw128(0, kKVBlockBytes, 1024);      // V: MN-major, see below
+      LA_PROF_DECL(5);
+      auto issue_qk = [&](int i, int s) {
+        LA_CLK(k0);
         mbar_wait(bar(kBarKFull + s), (i >> 1) & 1, 2, i);
+        LA_CLK(k1);
+        LA_ACC(0, k0, k1);
         tc_fence_after();
-        const uint64_t k_desc = make_smem_desc_sw128(smem_base + kOffK + s * kKVBytes, 16, 1024);
-        const uint32_t d_tmem = tmem_base + kTmemS + s * kN;
+        if (elect_one_sync()) {
+          const uint32_t d_tmem = tmem_base + kTmemS + s * kN;
 #pragma unroll
-        for (int j = 0; j < kD / 16; ++j) {
-          // K-major SW128: 4 k-steps of 32 B inside a 128 B swizzle row, then the next 64-column block.
-          const uint32_t a_off = ((j >> 2) * kQBlockBytes + (j & 3) * 32) >> 4;
-          const uint32_t b_off = ((j >> 2) * kKVBlockBytes + (j & 3) * 32) >> 4;
-          umma_ss(d_tmem, q_desc + a_off, k_desc + b_off, kIdescQK, j > 0);
+          for (int j = 0; j < kD / 16; ++j) {
+            // K-major SW128: 4 k-steps of 32 B inside a 128 B swizzle row, then the next 64-column block.
+            const uint32_t a_off = ((j >> 2) * kQBlockBytes + (j & 3) * 32) >> 4;
+            const uint32_t b_off = (s * kKVBytes + (j >> 2) * kKVBlockBytes + (j & 3) * 32) >> 4;
+            umma_ss(d_tmem, kDescKMajorHi | (uint64_t)(q_lo + a_off), kDescKMajorHi | (uint64_t)(k_lo + b_off),
+                    kIdescQK, j > 0);
+          }
+          tc_commit(bar(kBarKEmpty + s));  // K stage reusable once these MMAs retire
+          tc_commit(bar(kBarSFull + s));   // S(i) ready for the softmax warps
         }
-        tc_commit(bar(kBarKEmpty + s));  // K stage reusable once these MMAs retire
-        tc_commit(bar(kBarSFull + s));   // S(i) ready for the softmax warps
+        __syncwarp();
+        LA_CLK(k2);
+        LA_ACC(1, k1, k2);
+      };
+      auto issue_pv = [&](int i, int s) {
+        LA_CLK(v0);
+        mbar_wait(bar(kBarVFull + s), (i >> 1) & 1, 4, i);
+        LA_CLK(v1);
+        mbar_wait(bar(kBarPFull + s), (i >> 1) & 1, 5, i);
+        LA_CLK(v2);
+        LA_ACC(2, v0, v1);
+        LA_ACC(3, v1, v2);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          // V tile is [176 kv rows][64 d] x 2 blocks, i.e. the MN-major B operand:
+          //   LBO = distance between the two 64-wide d blocks, SBO = 8 kv rows (1024 B); one k-step = 16 rows.
+          const uint32_t p_tmem = tmem_base + kTmemS + s * kN;
+          umma_ts(tmem_base + kTmemO, p_tmem, kDescVHi | (uint64_t)(v_lo + ((s * kKVBytes) >> 4)), kIdescPV, i > 0);
+#pragma unroll
+          for (int j = 1; j < kN / 16; ++j) {
+            umma_ts(tmem_base + kTmemO, p_tmem + j * 8,
+                    kDescVHi | (uint64_t)(v_lo + ((s * kKVBytes + j * 16 * 128) >> 4)), kIdescPV, 1);
+          }
+          tc_commit(bar(kBarVEmpty + s));
+          tc_commit(bar(kBarPvDone));
+          // Not kBarPvDone: a parity wait is only meaningful one phase behind, and the speculative tiles never
+          // wait on it, so by the epilogue that barrier may be two phases ahead of a warp's last wait.
+          if (i == Tu - 1) tc_commit(bar(kBarOFull));
+        }
+        __syncwarp();
+        LA_CLK(v3);
+        LA_ACC(4, v2, v3);
       };
       mbar_wait(bar(kBarQFull), 0, 3, 0);
-      issue_qk(0);
-      for (int i = 0; i < T; ++i) {
-        if (i + 1 < T) issue_qk(i + 1);
-        const int s = i & 1;
-        mbar_wait(bar(kBarVFull + s), (i >> 1) & 1, 4, i);
-        mbar_wait(bar(kBarPFull + s), (i >> 1) & 1, 5, i);
-        tc_fence_after();
-        // V tile is [176 kv rows][64 d] x 2 blocks, i.e. the MN-major B operand:
-        //   LBO = distance between the two 64-wide d blocks, SBO = 8 kv rows (1024 B); one k-step = 16 rows.
-        const uint64_t v_desc = make_smem_desc_sw128(smem_base + kOffV + s * kKVBytes, kKVBlockBytes, 1024);
-        const uint32_t p_tmem = tmem_base + kTmemS + s * kN;
-#pragma unroll
-        for (int j = 0; j < kN / 16; ++j) {
-          umma_ts(tmem_base + kTmemO, p_tmem + j * 8, v_desc + ((j * 16 * 128) >> 4), kIdescPV, (i > 0) || (j > 0));
+      issue_qk(0, 0);
+      for (int i = 0; i < Tu; i += 2) {   // two tiles per trip so that the stage index is a compile-time constant
+        if (i + 1 < Tu) issue_qk(i + 1, 1);
+        issue_pv(i, 0);
+        if (i + 1 < Tu) {
+          if (i + 2 < Tu) issue_qk(i + 2, 0);
+          issue_pv(i + 1, 1);
         }
-        tc_commit(bar(kBarVEmpty + s));
-        tc_commit(bar(kBarPvDone));
-        // Not kBarPvDone: a parity wait is only meaningful one phase behind, and the speculative tiles never
-        // wait on it, so by the epilogue that barrier may be two phases ahead of a warp's last wait.
-        if (i == T - 1) tc_commit(bar(kBarOFull));
       }
+      if (lane == 0) { LA_PROF_FLUSH(8, 5); }
     }
     __syncwarp();
+  }
   } else {
     // ================================================================ softmax warps (256 threads)
+    setmaxnreg_inc<kRegsSoftmax>();
     const int wg = warp >> 2;                 // column half: 0 -> S[:, 0:88), 1 -> S[:, 88:176)
     const int row = (warp & 3) * 32 + lane;   // TMEM lane == query row inside the tile
     const int tid = threadIdx.x;              // 0..255
@@ -407,114 +479,209 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     const uint32_t pair_bar = 1 + (warp & 3);
     const uint64_t c2 = pack2(c, c);
 
-    for (int i = 0; i < T; ++i) {
-      const int buf = i & 1;
-      mbar_wait(bar(kBarSFull + buf), (i >> 1) & 1, 6, i);
-      tc_fence_after();
+    // QK-skip statistic of a tile: (m_local - m_prev) * scale_log2 (softmax.h:194) reduced with max over the tile's
+    // 128 rows (one warp-level redux + one shared-memory reduction per warp).  It is emitted one tile late, inside
+    // the next tile's exponential phase, where its latency is free; the two column halves alternate tiles.
+    float stat_d = 0.f;    // this row's (m_local - m_prev) * c of the previous tile
+    int stat_i = 0;        // its visit index (0 = nothing pending: the first visited tile has no statistic)
+    auto emit_stat = [&]() {
+      if (stat_i > 0 && (stat_i & 1) == wg) {
+        int od = (stat_d != stat_d) ? float_to_ordered(-INFINITY) : float_to_ordered(stat_d);  // NaN compares false upstream
+        od = __reduce_max_sync(0xffffffffu, od);
+        if (lane == 0) red_smax_s32(stat_base + stat_i * 4, od);
+      }
+    };
 
-      const uint32_t s_addr = tmem_base + kTmemS + buf * kN + wg * kHalfN + lane_field;
+    // Raw S of the tile being processed (this thread's 88 columns).  It is (re)loaded at the END of the previous
+    // tile's iteration -- after that tile's P stores were issued and, on the exact path, after the out-of-line
+    // call -- so the TMEM read latency of tile i+1 hides under the tail of tile i and the array is never live
+    // across the call.
+    float s[kHalfN];
+    uint32_t* sr = reinterpret_cast<uint32_t*>(s);
+    auto s_tmem = [&](int i) { return tmem_base + kTmemS + (i & 1) * kN + wg * kHalfN + lane_field; };
+    auto load_s = [&](int i) {
+      const uint32_t a = s_tmem(i);
+      tc_fence_after();
+      tmem_ld_x32(a, sr);
+      tmem_ld_x32(a + 32, sr + 32);
+      tmem_ld_x16(a + 64, sr + 64);
+      tmem_ld_x8(a + 80, sr + 80);
+    };
+    // Named barriers of the warp pair that owns the same 32 rows (ids 1..8; 0 is __syncthreads), split so that
+    // posting a half-row max never blocks: a warp ARRIVES on its tx barrier when its max is in smem -- which also
+    // says "all my S columns are in registers", the condition for the partner's P to land on them -- and SYNCS on
+    // the partner's when it needs the full-row max.
+    const uint32_t xchg_tx = 1 + (warp & 3) + 4 * wg;
+    const uint32_t xchg_rx = 1 + (warp & 3) + 4 * (wg ^ 1);
+    auto exact_tile = [&](int i, float m_loc_known) -> float {
+      const int buf = i & 1;
+      SlowTileArgs a;
+      a.s_addr = s_tmem(i);
+      a.p_addr = tmem_base + kTmemS + buf * kN + wg * (kHalfN / 2) + lane_field;
+      a.o_addr = tmem_base + kTmemO + wg * 64 + lane_field;
+      a.xchg_mine = xchg_base + (buf * kSoftmaxThreads + tid) * 4;
+      a.xchg_other = xchg_base + (buf * kSoftmaxThreads + (tid ^ 128)) * 4;
+      a.bar_tx = xchg_tx;
+      a.bar_rx = xchg_rx;
+      a.bar_pv_done = bar(kBarPvDone);
+      a.i = i;
+      // Key columns >= seqlen_k are masked in the FIRST processed tile only (mask.h:66-76, mainloop :1626).
+      a.mask_lim = (i == 0) ? args.seqlen_k - (seq[0] * kN + wg * kHalfN) : kHalfN;
+      a.c = c;
+      a.m_loc = m_loc_known;
+      a.have_mloc = (i != 0);
+      a.m_true = m_true;
+      a.m_ref = m_ref;
+      a.l_run = l_run;
+      softmax_slow_tile(&a);
+      m_ref = a.m_ref;
+      l_run = a.l_run;
+      return a.m_loc;
+    };
+    auto publish_p = [&](int i) {   // P(i) is in TMEM (and O rescaled if it had to be): let the issuer run PV(i)
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(kBarPFull + (i & 1)));
+    };
+
+    LA_PROF_DECL(7);
+    if (T > 0) {
+      // ---------------- first visited tile: always exact (there is no reference yet)
+      mbar_wait(bar(kBarSFull + 0), 0, 6, 0);
+      tc_fence_after();
+      m_true = exact_tile(0, 0.f);
+      publish_p(0);
+      if (T > 1) {
+        mbar_wait(bar(kBarSFull + 1), 0, 6, 1);
+        load_s(1);
+      }
+    }
+    for (int i = 1; i < T; ++i) {
+      const int buf = i & 1;
       // P (bf16 pairs) goes over the first 88 columns of this S buffer: wg0 -> [0,44), wg1 -> [44,88).
-      // Safe: it is stored only after both half-row owners have read S (named barrier below).
       const uint32_t p_addr = tmem_base + kTmemS + buf * kN + wg * (kHalfN / 2) + lane_field;
       const uint32_t xchg_mine = xchg_base + (buf * kSoftmaxThreads + tid) * 4;
       const uint32_t xchg_other = xchg_base + (buf * kSoftmaxThreads + (tid ^ 128)) * 4;
-
-      float m_loc;
-      bool slow = (i == 0);
-      if (!slow) {
-        // ---------------- speculative tile: exponentials against the current reference, row max on the side
-        float s[kHalfN];
-        uint32_t* sr = reinterpret_cast<uint32_t*>(s);
-        tmem_ld_x32(s_addr, sr);
-        tmem_ld_x32(s_addr + 32, sr + 32);
-        tmem_ld_x16(s_addr + 64, sr + 64);
-        tmem_ld_x8(s_addr + 80, sr + 80);
-        tmem_wait_ld();
-
-        const float neg_mc = -m_ref * c;
-        const uint64_t nm2 = pack2(neg_mc, neg_mc);
-        uint32_t pr[kHalfN / 2];
-        uint64_t acc0 = pack2(0.f, 0.f), acc1 = pack2(0.f, 0.f);
-        float mx0 = -INFINITY, mx1 = -INFINITY;
+      const uint32_t next_bar = bar(kBarSFull + (buf ^ 1));
+      const uint32_t next_par = ((i + 1) >> 1) & 1;
+      const bool more = i + 1 < T;
+#ifdef LA_EXPERIMENT_MMAONLY   // timing experiment only (wrong results): no softmax work at all, P = whatever is in TMEM
+      tmem_wait_ld();
+      publish_p(i);
+      if (more) { mbar_wait(next_bar, next_par, 6, i + 1); load_s(i + 1); }
+      continue;
+#endif
+      // ---------------- speculative tile: exponentials against the current reference, row max on the side
+      LA_CLK(t0);
+      tmem_wait_ld();
+      LA_CLK(t1);
+      LA_ACC(0, t0, t1);
+      const float neg_mc = -m_ref * c;
+      const uint64_t nm2 = pack2(neg_mc, neg_mc);
+      uint32_t pr[kHalfN / 2];
+      uint64_t acc0 = pack2(0.f, 0.f), acc1 = pack2(0.f, 0.f);
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+      float m_half = 0.f;
+      constexpr int kQuads = kHalfN / 4;   // 22 groups of 4 columns
 #pragma unroll
-        for (int j = 0; j < kHalfN; j += 4) {
-          mx0 = fmax3(mx0, s[j], s[j + 1]);
-          mx1 = fmax3(mx1, s[j + 2], s[j + 3]);
-          float t0, t1, t2, t3, p0, p1, p2, p3;
-          unpack2(ffma2(pack2(s[j], s[j + 1]), c2, nm2), t0, t1);
-          unpack2(ffma2(pack2(s[j + 2], s[j + 3]), c2, nm2), t2, t3);
-          if ((kPolyMask >> ((j >> 1) & 7)) & 1u) {
-            exp2_poly_pair(t0, t1, p0, p1);
-          } else {
-            p0 = ex2_approx(t0);
-            p1 = ex2_approx(t1);
-          }
-          if ((kPolyMask >> (((j >> 1) + 1) & 7)) & 1u) {
-            exp2_poly_pair(t2, t3, p2, p3);
-          } else {
-            p2 = ex2_approx(t2);
-            p3 = ex2_approx(t3);
-          }
-          acc0 = fadd2(acc0, pack2(p0, p1));   // row sum uses fp32 P, before bf16 rounding (softmax.h:263-273)
-          acc1 = fadd2(acc1, pack2(p2, p3));
-          pr[j / 2] = pack_bf16(p0, p1);
-          pr[j / 2 + 1] = pack_bf16(p2, p3);
+      for (int q = 0; q < kQuads; ++q) {
+        const int j = 4 * q;
+        // The row max runs twice as fast as the exponentials (8 columns per trip): it is complete, in smem and
+        // announced to the partner by the middle of this loop, so the exchange latency hides under the rest.
+#ifndef LA_POST_AT_END
+        if (q < kQuads / 2) {
+          mx0 = fmax3(mx0, s[8 * q], s[8 * q + 1]);
+          mx1 = fmax3(mx1, s[8 * q + 2], s[8 * q + 3]);
+          mx0 = fmax3(mx0, s[8 * q + 4], s[8 * q + 5]);
+          mx1 = fmax3(mx1, s[8 * q + 6], s[8 * q + 7]);
         }
-        const float m_half = fmaxf(mx0, mx1);
-        // Exchange the half-row maxima between the two warps that own the same 32 rows.
-        sts_f32(xchg_mine, m_half);
-        named_bar_sync(pair_bar, 64);
-        m_loc = fmaxf(m_half, lds_f32(xchg_other));
-        // Both warps of the pair see the same m_loc and m_ref for the same rows => the same verdict.
-        slow = __any_sync(0xffffffffu, !((m_loc - m_ref) * c <= kLazyTau));
-        if (!slow) {
-          float a0, a1, a2, a3;
-          unpack2(acc0, a0, a1);
-          unpack2(acc1, a2, a3);
-          l_run += (a0 + a1) + (a2 + a3);
-          tmem_st_x32(p_addr, pr);
-          tmem_st_x8(p_addr + 32, pr + 32);
-          tmem_st_x4(p_addr + 40, pr + 40);
-          tmem_wait_st();
+        if (q == kQuads / 2) {
+          m_half = fmaxf(mx0, mx1);
+          sts_f32(xchg_mine, m_half);
+          named_bar_arrive(xchg_tx, 64);
+          emit_stat();   // of tile i-1
         }
+#else
+        mx0 = fmax3(mx0, s[j], s[j + 1]);
+        mx1 = fmax3(mx1, s[j + 2], s[j + 3]);
+        if (q == kQuads / 2) emit_stat();   // of tile i-1
+#endif
+        float t0, t1, t2, t3, p0, p1, p2, p3;
+        unpack2(ffma2(pack2(s[j], s[j + 1]), c2, nm2), t0, t1);
+        unpack2(ffma2(pack2(s[j + 2], s[j + 3]), c2, nm2), t2, t3);
+        if ((kPolyMask >> ((j >> 1) & 7)) & 1u) {
+          exp2_poly_pair(t0, t1, p0, p1);
+        } else {
+          p0 = ex2_approx_ordered(t0);
+          p1 = ex2_approx_ordered(t1);
+        }
+        if ((kPolyMask >> (((j >> 1) + 1) & 7)) & 1u) {
+          exp2_poly_pair(t2, t3, p2, p3);
+        } else {
+          p2 = ex2_approx_ordered(t2);
+          p3 = ex2_approx_ordered(t3);
+        }
+        acc0 = fadd2(acc0, pack2(p0, p1));   // row sum uses fp32 P, before bf16 rounding (softmax.h:263-273)
+        acc1 = fadd2(acc1, pack2(p2, p3));
+        pr[j / 2] = pack_bf16(p0, p1);
+        pr[j / 2 + 1] = pack_bf16(p2, p3);
       }
-      if (slow) {
-        SlowTileArgs a;
-        a.s_addr = s_addr;
-        a.p_addr = p_addr;
-        a.o_addr = tmem_base + kTmemO + wg * 64 + lane_field;
-        a.xchg_mine = xchg_mine;
-        a.xchg_other = xchg_other;
-        a.bar_id = pair_bar;
-        a.bar_pv_done = bar(kBarPvDone);
-        a.i = i;
-        // Key columns >= seqlen_k are masked in the FIRST processed tile only (mask.h:66-76, mainloop :1626).
-        a.mask_lim = (i == 0) ? args.seqlen_k - (seq[0] * kN + wg * kHalfN) : kHalfN;
-        a.c = c;
-        a.m_loc = m_loc;
-        a.have_mloc = (i != 0);
-        a.m_true = m_true;
-        a.m_ref = m_ref;
-        a.l_run = l_run;
-        softmax_slow_tile(&a);
-        m_loc = a.m_loc;
-        m_ref = a.m_ref;
-        l_run = a.l_run;
+#ifdef LA_POST_AT_END
+      m_half = fmaxf(mx0, mx1);
+      sts_f32(xchg_mine, m_half);
+      named_bar_arrive(xchg_tx, 64);
+#endif
+      // Is S(i+1) there yet?  (Asked here so that the answer's latency runs under the verdict.)
+      const bool ready = more && mbar_try_wait(next_bar, next_par);
+      LA_CLK(t2);
+      LA_ACC(1, t1, t2);
+      named_bar_sync(xchg_rx, 64);
+      float m_loc = fmaxf(m_half, lds_f32(xchg_other));
+      // Both warps of the pair see the same m_loc and m_ref for the same rows => the same verdict.
+      const bool exact = __any_sync(0xffffffffu, !((m_loc - m_ref) * c <= kLazyTau));
+      LA_CLK(t3);
+      LA_ACC(2, t2, t3);
+      if (!exact) {
+        float a0, a1, a2, a3;
+        unpack2(acc0, a0, a1);
+        unpack2(acc1, a2, a3);
+        l_run += (a0 + a1) + (a2 + a3);
+        tmem_st_x32(p_addr, pr);
+        tmem_st_x8(p_addr + 32, pr + 32);
+        tmem_st_x4(p_addr + 40, pr + 40);
+        if (ready) load_s(i + 1);   // S(i+1)'s read latency runs under the publication of P(i)
+        LA_CLK(t4);
+        LA_ACC(3, t3, t4);
+        publish_p(i);
+        if (more && !ready) {
+          mbar_wait(next_bar, next_par, 6, i + 1);
+          load_s(i + 1);
+        }
+        LA_CLK(t8);
+        LA_ACC(4, t4, t8);
+      } else {
+        LA_CLK(t5);
+        m_loc = exact_tile(i, m_loc);
+        publish_p(i);
+        if (more) {
+          mbar_wait(next_bar, next_par, 6, i + 1);
+          load_s(i + 1);
+        }
+        LA_CLK(t6);
+        LA_ACC(5, t5, t6);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(kBarPFull + buf));
-
-      // ---------------- off the critical path: QK-skip statistic and the true running max
-      if (wg == 0 && i > 0) {
-        // (m_local - m_prev) * scale_log2 (softmax.h:194), reduced with max over the tile's 128 rows.
-        const float d = __fmul_rn(__fsub_rn(m_loc, m_true), c);
-        int od = (d != d) ? float_to_ordered(-INFINITY) : float_to_ordered(d);  // NaN compares false upstream
-        od = __reduce_max_sync(0xffffffffu, od);
-        if (lane == 0) red_smax_s32(stat_base + i * 4, od);
-      }
+      stat_d = __fmul_rn(__fsub_rn(m_loc, m_true), c);
+      stat_i = i;
       m_true = fmaxf(m_true, m_loc);
+#ifdef LA_PROFILE_CLOCKS
+      prof_acc[6] += 1;
+#endif
     }
+    emit_stat();   // of the last tile
+#ifdef LA_PROFILE_CLOCKS
+    if (lane == 0 && (warp == 0 || warp == 4)) { LA_PROF_FLUSH(warp == 0 ? 0 : 20, 7); }
+#endif
 
     // ---------------------------------------------------------------- epilogue
     float inv = 0.f, lse = -INFINITY;

@@ -47,7 +47,10 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 #endif
 __device__ unsigned int g_la_watchdog[4];  // [0]=flag, [1]=site id, [2]=blockIdx.x, [3]=parity|iter
 
-__device__ __noinline__ void la_watchdog_fail(int site, int iter, uint32_t parity) {
+// Inline on purpose (cold, but NOT a call): a call inside the wait loop makes every value that is live across a
+// wait -- e.g. 88 prefetched S registers in the softmax warps -- subject to the ABI's caller-saved set, and ptxas
+// then spills them to local memory in the hot loop.
+__device__ __forceinline__ void la_watchdog_fail(int site, int iter, uint32_t parity) {
   if (atomicExch(&g_la_watchdog[0], 1u) == 0u) {
     g_la_watchdog[1] = (unsigned)site;
     g_la_watchdog[2] = blockIdx.x;
@@ -60,8 +63,34 @@ __device__ __noinline__ void la_watchdog_fail(int site, int iter, uint32_t parit
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int site = 0, int iter = 0) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > LA_WATCHDOG_SPINS) la_watchdog_fail(site, iter, parity);  // cold, out of line (I-cache)
+    if (++spins > LA_WATCHDOG_SPINS) la_watchdog_fail(site, iter, parity);
   }
+}
+
+// One lane of a converged warp (elect.sync): the idiom ptxas recognises around single-thread tcgen05 / TMA issue.
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %1;\n\t"
+      "@px mov.s32 %0, 1;\n\t}"
+      : "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred;
+}
+
+// Register re-allocation between warpgroups (all four warps of a warpgroup must execute it).
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() {
+#ifndef LA_NO_SETMAXNREG
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+#endif
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() {
+#ifndef LA_NO_SETMAXNREG
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+#endif
 }
 
 // ----------------------------------------------------------------------------- named barriers
@@ -184,6 +213,14 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int b_mn_ma
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Same instruction, but pinned in program order relative to the other volatile asm statements (barriers, TMEM
+// traffic): the softmax loop places a barrier arrive in the MIDDLE of its exponentials and the matching sync after
+// them, and nvcc is otherwise free to hoist that sync back up across the (pure) ex2 statements.
+__device__ __forceinline__ float ex2_approx_ordered(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 // ---- packed 2 x fp32 math (FFMA2 / FADD2 on sm_100a) -------------------------------------------------

@@ -11,6 +11,7 @@
 #include <cuda_bf16.h>
 
 #include "la_ptx.cuh"
+#include "la_tmem_ptx.cuh"
 
 using namespace la;
 
@@ -25,7 +26,11 @@ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
 }
 
 // mode: see main()
-__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int mode, int iters, int fill, Res* res) {
+// bg: what warps 0-7 do while warp 9 issues the MMA stream
+//   0 nothing  1 LDTM x32 back to back (S0/S1 region)  2 LDTM paced like the kernel (88 cols / warp / ~1400 clk)
+//   3 STTM x32 back to back into the (unused) columns 480-511   4 MUFU.EX2 loop   5 FFMA loop
+//   6 kernel-like mix: 88 cols LDTM + 88 ex2 + 44 cols STTM per ~tile
+__global__ void __launch_bounds__(320, 1) mma_rate_kernel(int mode, int iters, int fill, int bg, Res* res) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sb = smem_u32(smem);
@@ -60,7 +65,10 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int mode, int iters, i
   tc_fence_after();
   const uint32_t tm = tmem_slot;
 
-  if (threadIdx.x == 0) {
+  __shared__ volatile int stop_flag;
+  if (threadIdx.x == 0) stop_flag = 0;
+  __syncthreads();
+  if (threadIdx.x == 9 * 32) {
     const uint64_t q0 = make_smem_desc_sw128(sb + offQ0, 16, 1024);
     const uint64_t q1 = make_smem_desc_sw128(sb + offQ1, 16, 1024);
     const uint64_t kd = make_smem_desc_sw128(sb + offK, 16, 1024);
@@ -143,6 +151,40 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int mode, int iters, i
     mbar_wait(bar, 0);
     const long long t1 = clock64();
     res[blockIdx.x].cycles = (unsigned long long)(t1 - t0);
+    stop_flag = 1;
+  } else if (threadIdx.x < 256 && bg != 0) {
+    const int w = threadIdx.x >> 5;
+    const uint32_t lane_field = (uint32_t)((w & 3) * 32) << 16;
+    const uint32_t base = tm + lane_field + (w >> 2) * 88;
+    float acc = 0.f;
+    uint32_t r[32];
+    for (int j = 0; j < 32; ++j) r[j] = threadIdx.x + j;
+    long long next = clock64();
+    while (!stop_flag) {
+      if (bg == 1) {
+        tmem_ld_x32(base, r); tmem_ld_x32(base + 32, r); tmem_wait_ld();
+        acc += __uint_as_float(r[3]);
+      } else if (bg == 2 || bg == 6) {
+        tmem_ld_x32(base, r); tmem_wait_ld(); acc += __uint_as_float(r[1]);
+        if (bg == 6) { for (int j = 0; j < 32; ++j) acc += ex2_approx(__uint_as_float(r[j]) * 1e-30f); }
+        tmem_ld_x32(base + 32, r); tmem_wait_ld(); acc += __uint_as_float(r[2]);
+        if (bg == 6) { for (int j = 0; j < 32; ++j) acc += ex2_approx(__uint_as_float(r[j]) * 1e-30f); }
+        tmem_ld_x16(base + 64, r); tmem_ld_x8(base + 80, r + 16); tmem_wait_ld(); acc += __uint_as_float(r[3]);
+        if (bg == 6) {
+          for (int j = 0; j < 24; ++j) acc += ex2_approx(__uint_as_float(r[j]) * 1e-30f);
+          tmem_st_x32(tm + lane_field + 480, r); tmem_wait_st();
+        }
+        next += 1400;
+        while (clock64() < next && !stop_flag) {}
+      } else if (bg == 3) {
+        tmem_st_x32(tm + lane_field + 480, r); tmem_wait_st();
+      } else if (bg == 4) {
+        for (int j = 0; j < 32; ++j) acc += ex2_approx(acc * 1e-30f + j);
+      } else if (bg == 5) {
+        for (int j = 0; j < 32; ++j) acc = fmaf(acc, 1.0001f, 1e-9f * j);
+      }
+    }
+    if (acc == 123.456f) res[0].cycles = 0;
   }
   tc_fence_before();
   __syncthreads();
@@ -175,14 +217,18 @@ int main(int argc, char** argv) {
       {12, "2 tiles: QK QK PV PV", 2 * (8 * 88.0 + 11 * 64.0)},
       {14, "FA4-like tile: QK128 x8 + PV x8", 16 * 64.0},
   };
-  for (int fill = 0; fill < 2; ++fill) {
-    printf("---- operands %s\n", fill ? "random bf16 in [-1,1)" : "zero");
+  const int only_mode = argc > 2 ? atoi(argv[2]) : -1;
+  const int bg_max = argc > 3 ? atoi(argv[3]) : 0;
+  for (int bg = 0; bg <= bg_max; ++bg)
+  for (int fill = (only_mode >= 0 ? 1 : 0); fill < 2; ++fill) {
+    printf("---- operands %s, background work %d\n", fill ? "random bf16 in [-1,1)" : "zero", bg);
     for (const Mode& m : modes) {
+      if (only_mode >= 0 && m.id != only_mode) continue;
       cudaEvent_t e0, e1;
       cudaEventCreate(&e0); cudaEventCreate(&e1);
-      mma_rate_kernel<<<nsm, 128, kSmem>>>(m.id, 50, fill, d_res);  // warm
+      mma_rate_kernel<<<nsm, 320, kSmem>>>(m.id, 50, fill, bg, d_res);  // warm
       cudaEventRecord(e0);
-      mma_rate_kernel<<<nsm, 128, kSmem>>>(m.id, iters, fill, d_res);
+      mma_rate_kernel<<<nsm, 320, kSmem>>>(m.id, iters, fill, bg, d_res);
       cudaEventRecord(e1);
       cudaError_t err = cudaDeviceSynchronize();
       if (err != cudaSuccess) { printf("mode %d: %s\n", m.id, cudaGetErrorString(err)); return 1; }

@@ -1,5 +1,7 @@
 #!/usr/bin/env python3
-"""Cycle accounting of la_fwd_kernel (needs a library built with -DLA_PROFILE_CLOCKS at tools/_lib_prof.so)."""
+"""Cycle accounting of la_fwd_kernel.  Needs a -DLA_PROFILE_CLOCKS build:
+     python tools/build_variants.py prof=LA_PROFILE_CLOCKS
+     LITEATTN_B200_LIB=$PWD/tools/_build/lib_prof.so python tools/prof_clocks.py"""
 import ctypes, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from liteattention_b200 import _native as N
@@ -7,7 +9,7 @@ L = N.lib()
 B, S, H, D = 1, int(os.environ.get("S", 32768)), int(os.environ.get("H", 16)), 128
 q = torch.randn(B, S, H, D, device="cuda", dtype=torch.bfloat16); k = torch.randn_like(q); v = torch.randn_like(q)
 out = torch.empty_like(q); lse = torch.empty(B, H, S, device="cuda")
-buf = (ctypes.c_ulonglong * 16)()
+buf = (ctypes.c_ulonglong * 32)()
 for _ in range(2):
     N.fwd(q, k, v, out, lse, D ** -0.5)
 torch.cuda.synchronize()
@@ -16,16 +18,26 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(); N.fwd(q, k, v, out, lse, D ** -0.5); e1.record(); torch.cuda.synchronize()
 L.la_prof_read(buf, 1)
 v_ = list(buf)
-tiles = v_[15]
-ctas = H * ((S + 127) // 128)
-print(f"kernel {e0.elapsed_time(e1):.3f} ms, tiles {tiles}, per-SM tiles {tiles/148:.0f}")
-names = ["wait S", "pass1", "mbox wait+stat", "exp/alpha + pass2", "pvdone wait + rescale", "wait st + arrive"]
+tiles = v_[6]
+ms = e0.elapsed_time(e1)
+print(f"kernel {ms:.3f} ms ({4*B*H*S*S*D/ms/1e9:.0f} TFLOP/s), tiles {tiles}, per-SM tiles {tiles/148:.0f}, "
+      f"=> {ms*1e-3/(tiles/148)*1e9:.0f} ns per tile per SM")
+names = ["wait::ld S(i)", "exp loop (max posted mid-way) + try_wait", "xchg sync + verdict", "P st + prefetch issue", "publish", "exact tile (total)"]
+for base, tag in ((0, "warp 0 (cols 0-87)"), (20, "warp 4 (cols 88-175)")):
+    tot = 0
+    print(f" softmax {tag}")
+    for j, nm in enumerate(names):
+        per = v_[base + j] / max(tiles, 1)
+        tot += per
+        print(f"   {nm:28s} {per:8.0f} clk/tile")
+    print(f"   {'total':28s} {tot:8.0f} clk/tile")
+names = ["wait K full", "issue QK (8 MMA + 2 commit)", "wait V full", "wait P full", "issue PV (11 MMA + commits)"]
+print(" MMA warp")
 tot = 0
 for j, nm in enumerate(names):
-    per = v_[j] / tiles          # summed over the two WG leaders -> per tile (each tile handled by one WG)
-    tot += per
-    print(f"  softmax {nm:24s} {per:8.0f} cyc/tile")
-print(f"  softmax total per tile (one WG) {tot:8.0f}  => per-WG cycle for 2 tiles = {2*tot:.0f}")
-names = ["issue QK(i+1) incl. wait K", "wait V", "wait P", "issue PV"]
-for j, nm in enumerate(names):
-    print(f"  mma {nm:28s} {v_[8+j]/tiles:8.0f} cyc/tile")
+    per = v_[8 + j] / max(tiles, 1); tot += per
+    print(f"   {nm:28s} {per:8.0f} clk/tile")
+print(f"   {'total':28s} {tot:8.0f} clk/tile")
+print(" producer")
+for j, nm in enumerate(["wait K empty", "wait V empty"]):
+    print(f"   {nm:28s} {v_[16 + j] / max(tiles, 1):8.0f} clk/tile")

@@ -9,23 +9,34 @@
 //   reduced over the tile's 128 rows, which la_skip_update.cu turns into the next list.
 //
 // How (B200-first, nothing shared with the Hopper kernel):
-//   * 10 warps: 8 softmax warps (two warpgroups that split the 176 S columns 88/88, one TMEM lane = one
-//     query row per thread), 1 TMA producer warp, 1 tcgen05 issuer warp.
+//   * 12 warps: 8 softmax warps (two warpgroups that split the 176 S columns 88/88; one TMEM lane = one query row
+//     per thread), 1 TMA producer warp, 1 tcgen05 issuer warp (+2 idle warps that complete its warpgroup, so that
+//     setmaxnreg can move registers: 216 per softmax thread, 72 per producer/issuer thread).
 //   * Q (128x128), K and V tiles (176x128, 2 stages each) are TMA-loaded into 128B-swizzled smem.
 //   * S = Q K^T : tcgen05.mma kind::f16, M=128 N=176 K=16 x8, SS operands, fp32 accumulator in TMEM;
 //     two S buffers so QK^T of tile i+1 runs under the softmax of tile i.
 //   * P (bf16) is written back over S in TMEM and fed to O += P V as the TMEM A operand
 //     (M=128 N=128 K=16 x11, V is the MN-major smem B operand); O lives in TMEM for the whole CTA.
 //   * TMEM map (512 columns allocated): S0 @0, S1 @176, O @352..479.
-//   * O is rescaled in TMEM only when some row max of the warp actually moved (exact, not lazy).
-//   * Softmax math is packed (FFMA2 / FADD2 / FMNMX3) and S is read from TMEM exactly once.
+//   * The issuer warp walks its loop converged and issues through elect.sync, so descriptors sit in uniform
+//     registers (19 UTCHMMA per tile back to back instead of an ELECT + R2UR chain per instruction).
+//   * Softmax, per tile (tools/prof_clocks.py, tools/softmax_rate.cu, tools/issue_rate.cu give the budget: MUFU.EX2
+//     is 16/clk/SM = 1408 clk for a 128x176 tile, exactly the tile's MMA time; FFMA2/FADD2/FMNMX3/F2FP dispatch at
+//     one warp-instruction per 2 clk per SM sub-partition, 3 of them per element = ~1060 clk):
+//       - lazy scaling reference: P = 2^((S - m_ref) c) with m_ref trailing the TRUE running max by <= 8 (log2
+//         units); the exponentials never wait for the tile's own max and O is almost never rescaled.  The QK-skip
+//         statistic is always computed from the true running max.
+//       - the verdict (does any row max run ahead of m_ref by more than 8?) needs the full-row max: the two warps
+//         that own a row exchange half-row maxima through smem and a pair of split named barriers.  If it fails,
+//         the tile is redone exactly, out of line (softmax_slow_tile): m_ref := true max, l and O rescaled.
+//       - 2 of every 8 column pairs take their exp2 on the FMA pipe (Cody-Waite + cubic), which balances the MUFU
+//         pipe against instruction dispatch; S(i+1) is pulled from TMEM while P(i) is being published; the
+//         statistic of tile i is reduced inside tile i+1's exponential loop.
 //
-// Why this organisation (measured, see profiles/README.md): at the Wan shape the kernel runs AT THE 1 kW POWER
-// CAP (sw_power_cap active, ~1.6 GHz), so sustained throughput is set by energy per tile, not by schedule
-// tightness.  Two re-organisations that overlap the softmax phases better (tile ping-pong between warpgroups
-// with a two-pass TMEM softmax, then 16 softmax warps; both with part of exp2 moved to the FMA pipe) were
-// built, verified and measured: they raise the work per tile (second TMEM pass, polynomial exp2) and lose
-// 3-6 % sustained throughput against this version, which does the least work per tile.
+// Measured ceiling of this organisation (one 128-row Q tile per CTA, 512 TMEM columns = 2 x S(176) + O(128)):
+// the tensor pipe alone runs the tile's 19 MMAs at the 1408-clk floor (tools/mma_rate.cu), L2->smem delivers
+// 75-80 B/clk/SM against the 64 needed (tools/l2_rate.cu); the softmax chain S(i) -> P(i) is ~2000 clk, and with
+// only two S buffers PV(i) -> QK(i+2) cannot be decoupled from it.  See DESIGN.md section 3.1.
 #include <cuda_bf16.h>
 
 #include "la_kernels.h"
@@ -128,7 +139,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // MUFU.EX2 runs at 16/clk/SM: 128x176 exponentials take exactly as long as the tile's two MMAs (1408 clk), so a
 // share of them has to come off the MUFU pipe for the softmax to fit under the tensor pipe at all.
 #ifndef LA_POLY_MASK
-#define LA_POLY_MASK 0x00u   // measured on B200 (S=32768,H=16 sustained): 0/8 1077, 1/8 1041, 2/8 1005, 3/8 986 TFLOP/s
+#define LA_POLY_MASK 0x44u   // 2 of every 8 column pairs; tools/build_variants.py + tools/sustained.py A/B on one box picks it
 #endif
 constexpr uint32_t kPolyMask = LA_POLY_MASK;
 
@@ -582,31 +593,13 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       uint32_t pr[kHalfN / 2];
       uint64_t acc0 = pack2(0.f, 0.f), acc1 = pack2(0.f, 0.f);
       float mx0 = -INFINITY, mx1 = -INFINITY;
-      float m_half = 0.f;
       constexpr int kQuads = kHalfN / 4;   // 22 groups of 4 columns
 #pragma unroll
       for (int q = 0; q < kQuads; ++q) {
         const int j = 4 * q;
-        // The row max runs twice as fast as the exponentials (8 columns per trip): it is complete, in smem and
-        // announced to the partner by the middle of this loop, so the exchange latency hides under the rest.
-#ifndef LA_POST_AT_END
-        if (q < kQuads / 2) {
-          mx0 = fmax3(mx0, s[8 * q], s[8 * q + 1]);
-          mx1 = fmax3(mx1, s[8 * q + 2], s[8 * q + 3]);
-          mx0 = fmax3(mx0, s[8 * q + 4], s[8 * q + 5]);
-          mx1 = fmax3(mx1, s[8 * q + 6], s[8 * q + 7]);
-        }
-        if (q == kQuads / 2) {
-          m_half = fmaxf(mx0, mx1);
-          sts_f32(xchg_mine, m_half);
-          named_bar_arrive(xchg_tx, 64);
-          emit_stat();   // of tile i-1
-        }
-#else
         mx0 = fmax3(mx0, s[j], s[j + 1]);
         mx1 = fmax3(mx1, s[j + 2], s[j + 3]);
         if (q == kQuads / 2) emit_stat();   // of tile i-1
-#endif
         float t0, t1, t2, t3, p0, p1, p2, p3;
         unpack2(ffma2(pack2(s[j], s[j + 1]), c2, nm2), t0, t1);
         unpack2(ffma2(pack2(s[j + 2], s[j + 3]), c2, nm2), t2, t3);
@@ -627,11 +620,10 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         pr[j / 2] = pack_bf16(p0, p1);
         pr[j / 2 + 1] = pack_bf16(p2, p3);
       }
-#ifdef LA_POST_AT_END
-      m_half = fmaxf(mx0, mx1);
+      // Post this half's row max (which also tells the partner that all of our S columns are in registers).
+      const float m_half = fmaxf(mx0, mx1);
       sts_f32(xchg_mine, m_half);
       named_bar_arrive(xchg_tx, 64);
-#endif
       // Is S(i+1) there yet?  (Asked here so that the answer's latency runs under the verdict.)
       const bool ready = more && mbar_try_wait(next_bar, next_par);
       LA_CLK(t2);

@@ -40,31 +40,26 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
   return done;
 }
 
-// Watchdog: a protocol bug must not hang the GPU box; after ~2^24 failed polls the CTA records where it
-// was stuck and traps (the host then sees a launch failure instead of a timeout).
+// Watchdog: a protocol bug must not hang the GPU box; after ~2^24 failed polls the waiting thread traps and the host
+// sees a launch failure instead of a timeout (compute-sanitizer then names the wait, the build has -lineinfo).
+// Deliberately nothing but a counter and a trap: a recording call here costs 3 % of the forward kernel (code bloat
+// in every wait loop, and a call makes values live across a wait -- the prefetched S registers -- spill).
 #ifndef LA_WATCHDOG_SPINS
 #define LA_WATCHDOG_SPINS (1u << 24)
 #endif
-__device__ unsigned int g_la_watchdog[4];  // [0]=flag, [1]=site id, [2]=blockIdx.x, [3]=parity|iter
-
-// Inline on purpose (cold, but NOT a call): a call inside the wait loop makes every value that is live across a
-// wait -- e.g. 88 prefetched S registers in the softmax warps -- subject to the ABI's caller-saved set, and ptxas
-// then spills them to local memory in the hot loop.
-__device__ __forceinline__ void la_watchdog_fail(int site, int iter, uint32_t parity) {
-  if (atomicExch(&g_la_watchdog[0], 1u) == 0u) {
-    g_la_watchdog[1] = (unsigned)site;
-    g_la_watchdog[2] = blockIdx.x;
-    g_la_watchdog[3] = ((unsigned)iter << 1) | parity;
-    __threadfence_system();
-  }
-  __trap();
-}
+__device__ unsigned int g_la_watchdog[4];  // kept for ABI compatibility of la_watchdog_read (always zero)
 
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int site = 0, int iter = 0) {
+  (void)site;
+  (void)iter;
+#ifdef LA_NO_WATCHDOG
+  while (!mbar_try_wait(bar, parity)) {}
+#else
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > LA_WATCHDOG_SPINS) la_watchdog_fail(site, iter, parity);
+    if (++spins > LA_WATCHDOG_SPINS) __trap();
   }
+#endif
 }
 
 // One lane of a converged warp (elect.sync): the idiom ptxas recognises around single-thread tcgen05 / TMA issue.
@@ -82,15 +77,11 @@ __device__ __forceinline__ uint32_t elect_one_sync() {
 // Register re-allocation between warpgroups (all four warps of a warpgroup must execute it).
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() {
-#ifndef LA_NO_SETMAXNREG
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
-#endif
 }
 template <int N>
 __device__ __forceinline__ void setmaxnreg_dec() {
-#ifndef LA_NO_SETMAXNREG
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
-#endif
 }
 
 // ----------------------------------------------------------------------------- named barriers
@@ -220,7 +211,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // them, and nvcc is otherwise free to hoist that sync back up across the (pure) ex2 statements.
 __device__ __forceinline__ float ex2_approx_ordered(float x) {
   float y;
+#ifdef LA_EXPERIMENT_NOEXP   // timing experiment only (wrong results): what does the tile cost without MUFU?
+  asm volatile("add.f32 %0, %1, 0f3F800000;" : "=f"(y) : "f"(x));
+#else
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+#endif
   return y;
 }
 // ---- packed 2 x fp32 math (FFMA2 / FADD2 on sm_100a) -------------------------------------------------

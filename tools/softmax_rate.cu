@@ -33,7 +33,10 @@ __device__ __forceinline__ void exp2_poly_pair(float t0, float t1, float& p0, fl
 // 5: full fast-path body (ld, max, ffma2, ex2, fadd2, pack, st)            6: body without LDTM/STTM (regs only)
 // 7: LDTM 16x256b... (not implemented)
 template <uint32_t MASK>
-__global__ void __launch_bounds__(256, 1) k(int mode, int iters, int nwarps, unsigned long long* res, float* sink) {
+__global__ void __launch_bounds__(288, 1) k(int mode, int iters, int nwarps, unsigned long long* res, float* sink, int with_mma) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ volatile int stop_flag;
+  if (threadIdx.x == 0) stop_flag = 0;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5;
   if (warp == 0) { tmem_alloc(smem_u32(&tmem_slot), 512); tmem_relinquish(); }
@@ -43,7 +46,22 @@ __global__ void __launch_bounds__(256, 1) k(int mode, int iters, int nwarps, uns
   const uint32_t s_addr = tm + lane_field + (warp >> 2) * 88;
   const uint32_t p_addr = tm + lane_field + 352 + (warp >> 2) * 44;
   float acc = 0.f;
-  if (warp < nwarps) {
+  if (warp == 8) {
+    if (with_mma && (threadIdx.x & 31) == 0) {
+      uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+      const uint32_t sb = smem_u32(smem);
+      const uint64_t qd = make_smem_desc_sw128(sb, 16, 1024), kd = make_smem_desc_sw128(sb + 32768, 16, 1024);
+      const uint64_t vd = make_smem_desc_sw128(sb + 32768 + 45056, 176 * 128, 1024);
+      constexpr uint32_t idQK = make_idesc_bf16(128, 176, 0), idPV = make_idesc_bf16(128, 128, 1);
+      long long n = 0;
+      while (!stop_flag) {
+        for (int j = 0; j < 8; ++j) umma_ss(tm + (n & 1) * 176, qd + ((((j >> 2) * 16384 + (j & 3) * 32)) >> 4), kd + ((((j >> 2) * 22528 + (j & 3) * 32)) >> 4), idQK, j > 0);
+        for (int j = 0; j < 11; ++j) umma_ts(tm + 352, tm + ((n + 1) & 1) * 176 + j * 8, vd + ((j * 16 * 128) >> 4), idPV, 1);
+        ++n;
+      }
+      res[blockIdx.x * 8 + 7 + 148 * 8] = (unsigned long long)n;
+    }
+  } else if (warp < nwarps) {
     // init TMEM region with small values
     { uint32_t z[32]; for (int j = 0; j < 32; ++j) z[j] = __float_as_uint(-1.0f - 0.01f * j);
       tmem_st_x32(s_addr, z); tmem_st_x32(s_addr + 32, z); tmem_st_x32(s_addr + 56, z); tmem_wait_st(); }
@@ -104,6 +122,8 @@ __global__ void __launch_bounds__(256, 1) k(int mode, int iters, int nwarps, uns
     }
     const long long t1 = clock64();
     if ((threadIdx.x & 31) == 0) res[blockIdx.x * 8 + warp] = (unsigned long long)(t1 - t0);
+    __syncwarp();
+    if (threadIdx.x == 0) stop_flag = 1;
     sink[blockIdx.x * 256 + threadIdx.x] = acc;
   }
   tc_fence_before(); __syncthreads(); tc_fence_after();
@@ -113,19 +133,28 @@ __global__ void __launch_bounds__(256, 1) k(int mode, int iters, int nwarps, uns
 int main(int argc, char** argv) {
   const int iters = argc > 1 ? atoi(argv[1]) : 2000;
   unsigned long long* d_res; float* d_sink;
-  cudaMalloc(&d_res, 148 * 8 * 8); cudaMalloc(&d_sink, 148 * 256 * 4);
+  cudaMalloc(&d_res, 148 * 8 * 8 * 2 + 64); cudaMalloc(&d_sink, 148 * 256 * 4);
   const char* names[] = {"LDTM 88 cols/warp (x32,x32,x16,x8) + wait", "LDTM 3 x x32 + wait (96 cols)", "STTM 44 cols/warp + wait",
                          "88 MUFU.EX2 per warp", "LDTM + row max", "full fast-path body (ld..st)", "body, registers only",
                          "body, poly 1/8", "body, poly 2/8", "body, poly 3/8", "body, poly 4/8", "body, poly 8/8"};
-  for (int nw : {4, 8}) {
+  const int SM = 200 * 1024;
+  cudaFuncSetAttribute(k<0x00u>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);
+  cudaFuncSetAttribute(k<0x10u>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);
+  cudaFuncSetAttribute(k<0x44u>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);
+  cudaFuncSetAttribute(k<0x92u>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);
+  cudaFuncSetAttribute(k<0x55u>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);
+  cudaFuncSetAttribute(k<0xFFu>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);
+  for (int with_mma = 0; with_mma < 2; ++with_mma)
+  for (int nw : {8}) {
+    printf("---- concurrent tcgen05.mma stream: %s\n", with_mma ? "YES" : "no");
     for (int mode = 0; mode < 12; ++mode) {
       cudaMemset(d_res, 0, 148 * 8 * 8);
-      if (mode < 7) k<0x00u><<<148, 256>>>(mode, iters, nw, d_res, d_sink);
-      else if (mode == 7) k<0x10u><<<148, 256>>>(5, iters, nw, d_res, d_sink);
-      else if (mode == 8) k<0x44u><<<148, 256>>>(5, iters, nw, d_res, d_sink);
-      else if (mode == 9) k<0x92u><<<148, 256>>>(5, iters, nw, d_res, d_sink);
-      else if (mode == 10) k<0x55u><<<148, 256>>>(5, iters, nw, d_res, d_sink);
-      else k<0xFFu><<<148, 256>>>(5, iters, nw, d_res, d_sink);
+      if (mode < 7) k<0x00u><<<148, 288, SM>>>(mode, iters, nw, d_res, d_sink, with_mma);
+      else if (mode == 7) k<0x10u><<<148, 288, SM>>>(5, iters, nw, d_res, d_sink, with_mma);
+      else if (mode == 8) k<0x44u><<<148, 288, SM>>>(5, iters, nw, d_res, d_sink, with_mma);
+      else if (mode == 9) k<0x92u><<<148, 288, SM>>>(5, iters, nw, d_res, d_sink, with_mma);
+      else if (mode == 10) k<0x55u><<<148, 288, SM>>>(5, iters, nw, d_res, d_sink, with_mma);
+      else k<0xFFu><<<148, 288, SM>>>(5, iters, nw, d_res, d_sink, with_mma);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("err %s\n", cudaGetErrorString(e)); return 1; }
       std::vector<unsigned long long> h(148 * 8);

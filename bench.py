@@ -202,7 +202,7 @@ def main():
         fwd_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in ev)
         upd_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in ev)
         return {"sparsity": LiteAttention.sparsity(rl), "fwd_ms": fwd_ms, "update_ms": upd_ms,
-                "exec_flops": synth.flops_executed(rl, S, S, D), "rl": rl}
+                "exec_flops": synth.flops_executed(rl, S, S, D), "update_bytes": synth.update_bytes(rl, wl), "rl": rl}
 
     # ---- the step the contract times: public objects, batch-parallel, O gathered to rank 0 ----------------
     n_groups = args.groups if args.groups > 0 else (1 if world == 1 else 5)
@@ -315,7 +315,12 @@ def main():
                                     if peaks else "fallback"),
                     "frac_of_burst_peak": achieved / peak_burst, "kernel_ms": kt_main["fwd_ms"],
                     "exec_flops_per_launch": kt_main["exec_flops"],
-                    "update_kernel": {"ms": kt_main["update_ms"], "bound": "hbm"}}
+                    "update_kernel": {"ms": kt_main["update_ms"], "bound": "hbm",
+                                      "achieved": kt_main["update_bytes"] / (kt_main["update_ms"] * 1e-3) / 1e9,
+                                      "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s",
+                                      "frac": kt_main["update_bytes"] / (kt_main["update_ms"] * 1e-3) / 1e9
+                                              / peaks.get("hbm_gbs", 6650.0),
+                                      "bytes_per_launch": kt_main["update_bytes"]}}
         sweep = None
         if args.sweep:
             sweep = []

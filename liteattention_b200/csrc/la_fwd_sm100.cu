@@ -29,7 +29,7 @@
 //       - the verdict (does any row max run ahead of m_ref by more than 8?) needs the full-row max: the two warps
 //         that own a row exchange half-row maxima through smem and a pair of split named barriers.  If it fails,
 //         the tile is redone exactly, out of line (softmax_slow_tile): m_ref := true max, l and O rescaled.
-//       - 2 of every 8 column pairs take their exp2 on the FMA pipe (Cody-Waite + cubic), which balances the MUFU
+//       - every other column pair takes its exp2 on the FMA pipe (Cody-Waite + cubic), which balances the MUFU
 //         pipe against instruction dispatch; S(i+1) is pulled from TMEM while P(i) is being published; the
 //         statistic of tile i is reduced inside tile i+1's exponential loop.
 //
@@ -139,7 +139,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // MUFU.EX2 runs at 16/clk/SM: 128x176 exponentials take exactly as long as the tile's two MMAs (1408 clk), so a
 // share of them has to come off the MUFU pipe for the softmax to fit under the tensor pipe at all.
 #ifndef LA_POLY_MASK
-#define LA_POLY_MASK 0x44u   // 2 of every 8 column pairs; tools/build_variants.py + tools/sustained.py A/B on one box picks it
+#define LA_POLY_MASK 0x55u   // every other column pair; chosen by same-box A/B (tools/build_variants.py + tools/sustained.py)
 #endif
 constexpr uint32_t kPolyMask = LA_POLY_MASK;
 
@@ -177,7 +177,7 @@ struct SlowTileArgs {
   uint32_t p_addr;      // where this thread's 44 bf16x2 P columns go
   uint32_t o_addr;      // this thread's 64 O columns
   uint32_t xchg_mine, xchg_other;  // smem byte addresses of the half-row max exchange slots
-  uint32_t bar_tx, bar_rx;  // split named barriers of the warp pair owning these 32 rows (arrive on tx, sync on rx)
+  uint32_t bar_id;      // named barrier of the warp pair owning these 32 rows
   uint32_t bar_pv_done; // mbarrier: PV(i-1) retired
   int i;                // visit index of the tile
   int mask_lim;         // < kHalfN: columns >= mask_lim of this half are out of range (first tile only)
@@ -212,14 +212,12 @@ __device__ __noinline__ void softmax_slow_tile(SlowTileArgs* a) {
     }
     const float m_half = fmaxf(mx0, mx1);
     sts_f32(a->xchg_mine, m_half);
-    named_bar_arrive(a->bar_tx, 64);
-    named_bar_sync(a->bar_rx, 64);
+    named_bar_sync(a->bar_id, 64);
     m_loc = fmaxf(m_half, lds_f32(a->xchg_other));
     a->m_loc = m_loc;
   } else {
     // The partner warp's P lands on S columns this warp has just re-read: order its store after our load.
-    named_bar_arrive(a->bar_tx, 64);
-    named_bar_sync(a->bar_rx, 64);
+    named_bar_sync(a->bar_id, 64);
   }
   const float m_new = fmaxf(a->m_true, m_loc);
   const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
@@ -487,7 +485,6 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 
     const uint32_t xchg_base = smem_base + kOffXchg;
     const uint32_t stat_base = smem_base + kOffStat;
-    const uint32_t pair_bar = 1 + (warp & 3);
     const uint64_t c2 = pack2(c, c);
 
     // QK-skip statistic of a tile: (m_local - m_prev) * scale_log2 (softmax.h:194) reduced with max over the tile's
@@ -518,12 +515,12 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       tmem_ld_x16(a + 64, sr + 64);
       tmem_ld_x8(a + 80, sr + 80);
     };
-    // Named barriers of the warp pair that owns the same 32 rows (ids 1..8; 0 is __syncthreads), split so that
-    // posting a half-row max never blocks: a warp ARRIVES on its tx barrier when its max is in smem -- which also
-    // says "all my S columns are in registers", the condition for the partner's P to land on them -- and SYNCS on
-    // the partner's when it needs the full-row max.
-    const uint32_t xchg_tx = 1 + (warp & 3) + 4 * wg;
-    const uint32_t xchg_rx = 1 + (warp & 3) + 4 * (wg ^ 1);
+    // Named barrier of the warp pair that owns the same 32 rows (ids 1..4; 0 is __syncthreads).  Always a full
+    // rendezvous (bar.sync by both warps), never arrive + sync: with a split barrier a warp that runs ahead can
+    // contribute twice to one phase -- its arrive for tile i and its next use of the same id -- while its partner
+    // sits between two instructions (cold instruction cache is enough); the pair then stays one phase apart and
+    // the last sync never completes.  (Seen as a 1-in-15 hang on fresh processes; tools/flaky2.py.)
+    const uint32_t pair_bar = 1 + (warp & 3);
     auto exact_tile = [&](int i, float m_loc_known) -> float {
       const int buf = i & 1;
       SlowTileArgs a;
@@ -532,8 +529,7 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       a.o_addr = tmem_base + kTmemO + wg * 64 + lane_field;
       a.xchg_mine = xchg_base + (buf * kSoftmaxThreads + tid) * 4;
       a.xchg_other = xchg_base + (buf * kSoftmaxThreads + (tid ^ 128)) * 4;
-      a.bar_tx = xchg_tx;
-      a.bar_rx = xchg_rx;
+      a.bar_id = pair_bar;
       a.bar_pv_done = bar(kBarPvDone);
       a.i = i;
       // Key columns >= seqlen_k are masked in the FIRST processed tile only (mask.h:66-76, mainloop :1626).
@@ -620,15 +616,15 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         pr[j / 2] = pack_bf16(p0, p1);
         pr[j / 2 + 1] = pack_bf16(p2, p3);
       }
-      // Post this half's row max (which also tells the partner that all of our S columns are in registers).
+      // Exchange the half-row maxima between the two warps that own the same 32 rows.  Passing the barrier also
+      // means the partner has all of its S columns in registers, the condition for our P to land on them.
       const float m_half = fmaxf(mx0, mx1);
       sts_f32(xchg_mine, m_half);
-      named_bar_arrive(xchg_tx, 64);
       // Is S(i+1) there yet?  (Asked here so that the answer's latency runs under the verdict.)
       const bool ready = more && mbar_try_wait(next_bar, next_par);
       LA_CLK(t2);
       LA_ACC(1, t1, t2);
-      named_bar_sync(xchg_rx, 64);
+      named_bar_sync(pair_bar, 64);
       float m_loc = fmaxf(m_half, lds_f32(xchg_other));
       // Both warps of the pair see the same m_loc and m_ref for the same rows => the same verdict.
       const bool exact = __any_sync(0xffffffffu, !((m_loc - m_ref) * c <= kLazyTau));

@@ -111,31 +111,48 @@ __global__ void __launch_bounds__(kUpdWarpsPerBlock * 32) la_skip_update_kernel(
   if (!general) {
     // ---------------------------------------------------------------- fast path
     bool carry_ev = true;  // effective vote of the previous (higher) tile; irrelevant at range starts
-    for (int base = ktiles - 1; base >= 0; base -= 32) {
-      const int n = base - lane;
-      bool v = false, st = false, en = false;
-      if (n >= 0) {
-        const uint32_t bit = 1u << (n & 31);
-        v = vis[n >> 5] & bit;
-        st = smask[n >> 5] & bit;
-        en = emask[n >> 5] & bit;
+    // Four 32-tile chunks per trip: their statistic loads are issued together (the walk itself is a serial
+    // ballot/prefix chain, so without this every chunk would expose one full HBM latency).
+    constexpr int kUnroll = 4;
+    for (int base = ktiles - 1; base >= 0; base -= 32 * kUnroll) {
+      float sv[kUnroll];
+      bool vv[kUnroll], stt[kUnroll], enn[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int n = base - 32 * u - lane;
+        bool v = false, st = false, en = false;
+        if (n >= 0) {
+          const uint32_t bit = 1u << (n & 31);
+          v = vis[n >> 5] & bit;
+          st = smask[n >> 5] & bit;
+          en = emask[n >> 5] & bit;
+        }
+        vv[u] = v;
+        stt[u] = st;
+        enn[u] = en;
+        sv[u] = (v && n != first_n) ? __ldg(stat + n) : INFINITY;   // +inf > thr: "do", like the untested first tile
       }
-      bool rv = false;  // raw vote: true = skip
-      if (v && n != first_n) rv = !(stat[n] > thr);
-      const bool ev = rv;
-      bool prev_ev = __shfl_up_sync(0xffffffffu, ev, 1);
-      if (lane == 0) prev_ev = carry_ev;
-      const bool ps = st ? true : prev_ev;
-      const bool a = v && (ev != ps);
-      const bool b = v && en && !rv;
-      const uint32_t ma = __ballot_sync(0xffffffffu, a);
-      const uint32_t mb = __ballot_sync(0xffffffffu, b);
-      const uint32_t lt = (1u << lane) - 1u;
-      const int pos = w + __popc(ma & lt) + __popc(mb & lt);
-      if (a && pos <= ktiles) wr[pos] = n;
-      if (b && pos + (a ? 1 : 0) <= ktiles) wr[pos + (a ? 1 : 0)] = n;
-      w += __popc(ma) + __popc(mb);
-      carry_ev = __shfl_sync(0xffffffffu, ev, 31);
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int n = base - 32 * u - lane;
+        const bool v = vv[u], st = stt[u], en = enn[u];
+        bool rv = false;  // raw vote: true = skip
+        if (v && n != first_n) rv = !(sv[u] > thr);
+        const bool ev = rv;
+        bool prev_ev = __shfl_up_sync(0xffffffffu, ev, 1);
+        if (lane == 0) prev_ev = carry_ev;
+        const bool ps = st ? true : prev_ev;
+        const bool a = v && (ev != ps);
+        const bool b = v && en && !rv;
+        const uint32_t ma = __ballot_sync(0xffffffffu, a);
+        const uint32_t mb = __ballot_sync(0xffffffffu, b);
+        const uint32_t lt = (1u << lane) - 1u;
+        const int pos = w + __popc(ma & lt) + __popc(mb & lt);
+        if (a && pos <= ktiles) wr[pos] = n;
+        if (b && pos + (a ? 1 : 0) <= ktiles) wr[pos + (a ? 1 : 0)] = n;
+        w += __popc(ma) + __popc(mb);
+        carry_ev = __shfl_sync(0xffffffffu, ev, 31);
+      }
     }
     overflow = (w - 1) > ktiles;
   } else {

@@ -130,3 +130,18 @@ def flops_executed(read_list, seqlen_q, seqlen_k, d, batch=None):
     cols = (hi * is_start).sum(-1) - (lo * is_end).sum(-1)                    # [b,h,qt]
     rows = torch.clamp(seqlen_q - torch.arange(qt, device=rl.device) * BLOCK_M, max=BLOCK_M)
     return 4.0 * d * float((cols * rows.view(1, 1, qt)).sum().item())
+
+
+def update_bytes(read_list, write_list=None, batch=None):
+    """Algorithmic HBM bytes of one la_skip_update call: every row reads its list (len + 1 words) and
+    the statistic of each tile it visited, and writes the next list (len' + 1 words)."""
+    rl = (read_list if batch is None else read_list[:batch]).to(torch.int64)
+    wl = rl if write_list is None else (write_list if batch is None else write_list[:batch]).to(torch.int64)
+    kt = rl.shape[-1] - 1
+    ln = rl[..., 0].clamp(0, kt)
+    ent = rl[..., 1:]
+    pos = torch.arange(kt, device=rl.device)
+    valid = pos < ln.unsqueeze(-1)
+    visited = ((ent + 1) * ((pos % 2 == 0) & valid)).sum(-1) - (ent * ((pos % 2 == 1) & valid)).sum(-1)
+    words = (ln + 1).sum() + visited.sum() + (wl[..., 0].clamp(0, kt) + 1).sum()
+    return 4.0 * float(words.item())

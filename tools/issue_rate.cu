@@ -2,6 +2,7 @@
 // independent instruction streams: FFMA, FFMA2, FADD2, FMNMX3, F2FP, MUFU.EX2, IMAD and the mixes the softmax uses.
 #include <cstdio>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "la_ptx.cuh"
 using namespace la;
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -41,6 +42,22 @@ __global__ void __launch_bounds__(256, 1) k(int iters, int warps_per_smsp, long 
             b[(j + 4) & 7] = fadd2(b[(j + 4) & 7], pack2(p0, p1));
             a[j + 8] = __uint_as_float(pack_bf16(p0, p1));
           }
+          if (MODE == 12) {  // 2 MUFU.EX2.F16 (scalar half)
+            unsigned short h0 = __half_as_ushort(__float2half_rn(a[j])), h1 = __half_as_ushort(__float2half_rn(a[j + 8])), r0, r1;
+            asm volatile("ex2.approx.f16 %0, %1;" : "=h"(r0) : "h"(h0));
+            asm volatile("ex2.approx.f16 %0, %1;" : "=h"(r1) : "h"(h1));
+            a[j] = __half2float(__ushort_as_half(r0)); a[j + 8] = __half2float(__ushort_as_half(r1));
+          }
+          if (MODE == 13) {  // 1 ex2.approx.f16x2 (= 2 MUFU.EX2.F16 in SASS?)
+            unsigned int hh = (unsigned int)__float_as_uint(a[j]), rr;
+            asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(rr) : "r"(hh));
+            a[j] = __uint_as_float(rr);
+          }
+          if (MODE == 14) {  // 1 ex2.approx.ftz.bf16x2
+            unsigned int hh = (unsigned int)__float_as_uint(a[j]), rr;
+            asm volatile("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(rr) : "r"(hh));
+            a[j] = __uint_as_float(rr);
+          }
           if (MODE == 11) { a[j] = a[j] * 1.0001f + 0.5f; a[j + 8] = a[j + 8] * 0.9999f + 0.25f; }                           // 2 FFMA imm-form
         }
       }
@@ -75,5 +92,8 @@ int main() {
   run<8>("FFMA2 + MUFU", 2, d_res, d_sink);
   run<9>("FMNMX3 + MUFU", 2, d_res, d_sink);
   run<10>("softmax mix (6 instr / 2 elem)", 6, d_res, d_sink);
+  run<12>("MUFU.EX2.F16 x2 (+4 cvt)", 2, d_res, d_sink);
+  run<13>("ex2.approx.f16x2 (per PTX instr)", 1, d_res, d_sink);
+  run<14>("ex2.approx.ftz.bf16x2 (per PTX instr)", 1, d_res, d_sink);
   return 0;
 }

@@ -7,7 +7,7 @@ OUT=gpurun_out
 mkdir -p $OUT
 BENCH="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu"
 # every launch of the bench command with its device time (cold-cache, serialised: compare shares)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/launches_$TAG.csv $BENCH > $OUT/launches_$TAG.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:la_ -c 12 --csv --log-file $OUT/launches_$TAG.csv $BENCH > $OUT/launches_$TAG.log 2>&1
 # forward kernel at the Wan2.1-14B shape, 42 % sparsity (config C3/C4 direct variant)
 ncu --set full --clock-control none --import-source on -k regex:la_fwd_kernel -s 3 -c 1 -o $OUT/prof_fwd_wan42_$TAG -f $BENCH > $OUT/prof_fwd_wan42_$TAG.log 2>&1
 # forward kernel, config C2 (S=32768, H=16, fixed random 50 % mask)

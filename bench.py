@@ -40,6 +40,9 @@ def parse_args():
     ap.add_argument("--seq", type=int, default=S_WAN)
     ap.add_argument("--heads", type=int, default=H_WAN)
     ap.add_argument("--groups", type=int, default=0, help="head groups for the gather pipeline (0 = auto)")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N>1: peer = forward epilogue stores O into rank 0's symmetric buffer over NVLink (fused); "
+                         "nccl = NCCL gather pipelined by head group")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--sweep", action="store_true", help="also time sparsity 0/21/42/57/77 % (kernel only)")
@@ -209,7 +212,8 @@ def main():
 
     def factory():
         return LiteAttention(enable_skipping=True, threshold=float("-inf"), max_batch_size=B)
-    bp = BatchParallelLiteAttention(factory, num_heads=H, num_groups=n_groups, dst=0)
+    bp = BatchParallelLiteAttention(factory, num_heads=H, num_groups=n_groups, dst=0,
+                                    peer_store=(args.gather == "peer" and world > 1))
     for gi, gsl in enumerate(bp.groups):                         # preset every head group's list at the target sparsity
         bp.attn[gi].load_skip_list(make_list(args.sparsity, gsl.stop - gsl.start, seed=1234 + gi), q[:, :, gsl], v[:, :, gsl])
 
@@ -343,7 +347,7 @@ def main():
                                    "update" + ("" if world == 1 else f"; batch-parallel, O gathered to rank 0 over NCCL "
                                                                       f"in {n_groups} head groups"),
                        "batch_per_gpu": B, "seq_len": S, "heads": H, "head_dim": D, "sparsity": step_sparsity,
-                       "parallelism": f"batch-parallel x{world}",
+                       "parallelism": f"batch-parallel x{world}" + ("" if world == 1 else (", O stored by the forward epilogue into rank 0's symmetric buffer over NVLink (fused gather)" if args.gather == "peer" else ", NCCL gather pipelined by head group")),
                        "l2": "q/k/v/o = 3.1 GB per step >> 126 MB L2, no flush needed"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
         }

@@ -3,10 +3,20 @@ per-layer skip state, never communicated); the only collective is the gather of 
 (the reference has no distributed code on this path at all --
 `grep torch.distributed hopper/` is empty, SeqParallelLiteAttention is bookkeeping only).
 
-To keep the gather off the critical path the heads are processed in groups: the attention kernel of head
-group g+1 runs on the compute stream while group g's O slab is gathered on a side stream.  Only the last
-group's gather is exposed.  The attention callable is injectable so the sharding / pipelining logic can be
-exercised on CPU with the gloo backend (tests/test_dist_cpu.py).
+Two ways to get O to the destination rank:
+
+* fused ("peer store", the default on GPUs when torch symmetric memory is available): the destination's output
+  buffer [world, B, S, H, D] lives in symmetric memory; every rank maps it over NVLink/NVSwitch and passes ITS slot
+  as the forward kernel's `out` pointer, so the kernel's epilogue stores O straight into the destination GPU while
+  the other tiles are still computing -- compute and "gather" are one kernel, there is no collective kernel and no
+  exposed tail, only a device-side barrier at the end of the step.  (The forward kernel needs no change: its O
+  stores are plain 16-byte st.global from registers, a peer pointer is just a pointer.)
+* NCCL gather, pipelined by head group (the plumbing baseline and the CPU/gloo-testable path): the attention kernel
+  of head group g+1 runs on the compute stream while group g's O slab is gathered on a side stream; only the last
+  group's gather is exposed.
+
+The attention callable is injectable so the sharding / pipelining logic can be exercised on CPU with the gloo backend
+(tests/test_dist_cpu.py).
 """
 from typing import Callable, List, Optional
 
@@ -40,7 +50,11 @@ class BatchParallelLiteAttention:
     """
 
     def __init__(self, attn_factory: Callable[[], Callable], num_heads: int, num_groups: int = 5, dst: int = 0,
-                 group: Optional[dist.ProcessGroup] = None, gather: bool = True):
+                 group: Optional[dist.ProcessGroup] = None, gather: bool = True, peer_store: bool = False):
+        self.peer_store = bool(peer_store and gather and dist.is_initialized() and dist.get_world_size(group) > 1)
+        if self.peer_store:
+            num_groups = 1                      # nothing to overlap: the epilogue IS the transfer
+        self._symm = self._hdl = self._peer_slot = None
         self.groups = head_groups(num_heads, num_groups)
         self.attn = [attn_factory() for _ in self.groups]
         self.dst = dst
@@ -56,10 +70,27 @@ class BatchParallelLiteAttention:
             self._comm_stream = torch.cuda.Stream(device=device)
         return self._comm_stream
 
+    def _setup_peer(self, q: torch.Tensor):
+        import torch.distributed._symmetric_memory as symm_mem
+        shape = (self.world,) + tuple(q.shape)
+        pg = self.pg if self.pg is not None else dist.group.WORLD
+        self._symm = symm_mem.empty(shape, dtype=q.dtype, device=q.device)      # same size on every rank (symmetric)
+        self._hdl = symm_mem.rendezvous(self._symm, group=pg)
+        # rank r's view of slot r of the DESTINATION's buffer (peer memory mapped over NVLink)
+        self._peer_slot = self._hdl.get_buffer(self.dst, shape, q.dtype)[self.rank]
+
     def __call__(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor):
         """q, k, v: this rank's (B_local, S, H, D).  Returns (local O slabs per head group,
         gathered) where `gathered` is, on `dst`, a list over head groups of lists over ranks of
-        (B_local, S, Hg, D) tensors (None elsewhere / when not gathering)."""
+        (B_local, S, Hg, D) tensors (None elsewhere / when not gathering).  With peer_store the first element is
+        [this rank's slot of the destination buffer] and `gathered` is [[slot 0, slot 1, ...]] on `dst`."""
+        if self.peer_store:
+            if self._hdl is None:
+                self._setup_peer(q)
+            o = self.attn[0](q, k, v, out=self._peer_slot)
+            self._hdl.barrier()        # device-side, stream-ordered: every rank's stores have landed at dst
+            gathered = [[self._symm[r] for r in range(self.world)]] if self.rank == self.dst else None
+            return [o], gathered
         cuda = q.device.type == "cuda"
         comm = self._streams(q.device)
         outs, works = [], []

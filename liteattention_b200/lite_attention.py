@@ -17,7 +17,7 @@ from typing import Optional, Tuple, Union
 
 import torch
 
-from .flash_attn_interface import flash_attn_func
+from .flash_attn_interface import _flash_attn_forward, flash_attn_func
 
 
 class LiteAttention:
@@ -209,19 +209,32 @@ class LiteAttention:
     # ------------------------------------------------------------------ call
     def __call__(self, query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, scale: Optional[float] = None,
                  return_softmax_lse: bool = False, must_do_list: list = None,
-                 must_skip_list: list = None) -> Union[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
+                 must_skip_list: list = None, *, out: Optional[torch.Tensor] = None
+                 ) -> Union[torch.Tensor, Tuple[torch.Tensor, torch.Tensor]]:
         """query/key/value: (batch, seq_len, heads, head_dim) bf16.  Returns the attention output
         (batch, seq_len, heads, head_dim) [and softmax_lse (batch, heads, seq_len) fp32].
-        must_do_list: token ranges [start0, end0, start1, end1, ...] (descending) that may never be skipped."""
+        must_do_list: token ranges [start0, end0, start1, end1, ...] (descending) that may never be skipped.
+        out (extension, keyword-only; the reference's op takes it, `flash_api.cpp:861-870`, its Python does not pass
+        it): write the result there instead of allocating -- any device-visible bf16 (batch, seq_len, heads,
+        head_dim) buffer, including a peer GPU's memory mapped over NVLink (liteattention_b200/dist.py)."""
         read_list, write_list = self._get_read_write_lists(query, value, must_skip_list)
 
         must_do_list_expanded = None
         if self.enable_skipping and must_do_list is not None:
             must_do_list_expanded = self._must_do_expanded(must_do_list, write_list.shape, query, value)
 
-        output = flash_attn_func(q=query, k=key, v=value, softmax_scale=scale, attn_read_list=read_list,
-                                 attn_must_do_list=must_do_list_expanded, attn_write_list=write_list,
-                                 thr=self.threshold, return_softmax_lse=return_softmax_lse)
+        if out is None:
+            output = flash_attn_func(q=query, k=key, v=value, softmax_scale=scale, attn_read_list=read_list,
+                                     attn_must_do_list=must_do_list_expanded, attn_write_list=write_list,
+                                     thr=self.threshold, return_softmax_lse=return_softmax_lse)
+        else:
+            o, lse, *_ = _flash_attn_forward(
+                query, key, value, None, None, None, out, None, None, None, None, None, None, None, None, None, None,
+                None, None, None, None, None, None,
+                scale if scale is not None else query.shape[-1] ** (-0.5), causal=False,
+                attn_read_list=read_list, attn_must_do_list=must_do_list_expanded, attn_write_list=write_list,
+                thr=self.threshold)
+            output = (o, lse) if return_softmax_lse else o
 
         if self.enable_skipping and os.getenv("LITE_ATTENTION_VERBOSE", "FALSE") != "FALSE":
             real_batch_size = query.shape[0]

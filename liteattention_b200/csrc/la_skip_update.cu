@@ -59,7 +59,15 @@ __global__ void __launch_bounds__(kUpdWarpsPerBlock * 32) la_skip_update_kernel(
     }
     return;
   }
-  const int len = clamp_len(rd[0], ktiles);
+  // The row is walked through three dependent HBM round trips (length -> ranges -> statistic).  Fold the first two:
+  // the first 32 ranges are requested together with the length (a row always has ktiles + 1 >= 65 words here).
+  int pre_s = 0, pre_e = 0;
+  const bool can_pre = ktiles >= 64;
+  if (can_pre) {
+    pre_s = __ldg(rd + 1 + 2 * lane);
+    pre_e = __ldg(rd + 2 + 2 * lane);
+  }
+  const int len = clamp_len(__ldg(rd), ktiles);
   const int nranges = len >> 1;
   if (nranges == 0) {
     if (lane == 0) wr[0] = 0;
@@ -84,7 +92,8 @@ __global__ void __launch_bounds__(kUpdWarpsPerBlock * 32) la_skip_update_kernel(
     const int r = r0 + lane;
     bool bad = false;
     if (r < nranges) {
-      int s = rd[1 + 2 * r], e = rd[2 + 2 * r];
+      int s = (can_pre && r0 == 0) ? pre_s : rd[1 + 2 * r];
+      int e = (can_pre && r0 == 0) ? pre_e : rd[2 + 2 * r];
       s = min(s, ktiles - 1);
       e = max(e, 0);
       if (s < e) bad = true;                                   // empty after clamping: leave to the general path

@@ -126,3 +126,35 @@ def test_single_tile_rows(native_lib):
     assert got[0].tolist() == [2, 0] and got[1, 0] == 0
     exp, _ = H.c_oracle_step(read, None, stat, 0.0)
     assert exp[0].tolist() == [2, 0] and exp[1, 0] == 0
+
+
+@pytest.mark.gpu
+def test_threshold_calibration_hits_a_target_sparsity(native_lib):
+    """liteattention_b200.calibrate: bisection over the update kernel on a stored statistic; sparsity is monotone in
+    thr and the calibrated list is what a LiteAttention object with that threshold writes."""
+    import math
+    from liteattention_b200 import LiteAttention
+    from liteattention_b200.calibrate import calibrate_threshold
+    b, s, h = 1, 2600, 2
+    g = torch.Generator().manual_seed(5)
+    t = torch.arange(s).float()
+    w = torch.randn(128, generator=g) * 0.02
+    ph = torch.rand(128, generator=g) * 2 * math.pi
+    e = math.sqrt(2 / 128) * torch.cos(t[:, None] * w[None] + ph[None])
+    base = 16.0 * e[None, :, None, :].expand(b, s, h, 128)
+    q = (base + 0.5 * torch.randn(b, s, h, 128, generator=g)).to(torch.bfloat16).cuda()
+    k = (base + 0.5 * torch.randn(b, s, h, 128, generator=g)).to(torch.bfloat16).cuda()
+    v = torch.randn(b, s, h, 128, generator=g).to(torch.bfloat16).cuda()
+    prev = -1.0
+    thr_max, sp_max, _ = calibrate_threshold(q, k, v, 0.99)       # unreachable: the result at the upper bound comes back
+    assert thr_max == -1e-3 and 0.3 < sp_max < 0.99
+    for target in (0.1, 0.2, 0.3):
+        thr, sp, wl = calibrate_threshold(q, k, v, target)
+        assert thr < 0 and sp >= target and sp - target < 0.08, (target, thr, sp)
+        assert sp >= prev
+        prev = sp
+        la = LiteAttention(enable_skipping=True, threshold=thr, max_batch_size=b)
+        la(q, k, v)
+        kt1 = wl.shape[-1]   # entries beyond row[0] are stale by design (the writer never clears them)
+        assert H.rows_equal_upto_len(la.read_list[:b].cpu().view(-1, kt1).numpy(), wl.cpu().view(-1, kt1).numpy()), \
+            "calibrated list != list written by LiteAttention at that threshold"

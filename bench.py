@@ -325,6 +325,37 @@ def main():
                                       "frac": kt_main["update_bytes"] / (kt_main["update_ms"] * 1e-3) / 1e9
                                               / peaks.get("hbm_gbs", 6650.0),
                                       "bytes_per_launch": kt_main["update_bytes"]}}
+        # ---- the caller-side step in front of the kernel: fused 3-D RoPE + bf16 cast of Q, fp32 in
+        aux = None
+        try:
+            import math
+            from liteattention_b200.rope import rope_apply_bf16
+            half = D // 2
+            widths = [half - 2 * (half // 3), half // 3, half // 3]
+            ang = torch.cat([torch.outer(torch.arange(1024, dtype=torch.float64),
+                                         1.0 / torch.pow(10000.0, torch.arange(0, 2 * w_, 2, dtype=torch.float64) / (2 * w_)))
+                             for w_ in widths], dim=1)
+            freqs = torch.polar(torch.ones_like(ang), ang)
+            gf = 21 if S == S_WAN else max(1, S // (45 * 80))
+            grid_sizes = torch.tensor([[gf, 45, 80]] * B)
+            xq = torch.randn(B, S, H, D, device=dev, dtype=torch.float32)
+            for _ in range(3):
+                rope_apply_bf16(xq, grid_sizes, freqs)
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            for _ in range(10):
+                rope_apply_bf16(xq, grid_sizes, freqs)
+            r1.record()
+            torch.cuda.synchronize()
+            rms = r0.elapsed_time(r1) / 10
+            rbytes = xq.numel() * 6.0
+            aux = {"rope_cast_fp32_to_bf16": {"ms": rms, "bound": "hbm", "bytes_per_launch": rbytes,
+                                              "achieved": rbytes / (rms * 1e-3) / 1e9, "peak": peaks.get("hbm_gbs", 6650.0),
+                                              "unit": "GB/s", "frac": rbytes / (rms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0),
+                                              "note": "one Q (or K) tensor of the workload; 4 B read + 2 B written per element"}}
+            del xq
+        except Exception as e:  # noqa: BLE001  (auxiliary line only; the headline numbers do not depend on it)
+            aux = {"rope_cast_fp32_to_bf16": {"error": str(e)[:200]}}
         sweep = None
         if args.sweep:
             sweep = []
@@ -349,7 +380,7 @@ def main():
                        "batch_per_gpu": B, "seq_len": S, "heads": H, "head_dim": D, "sparsity": step_sparsity,
                        "parallelism": f"batch-parallel x{world}" + ("" if world == 1 else (", O stored by the forward epilogue into rank 0's symmetric buffer over NVLink (fused gather)" if args.gather == "peer" else ", NCCL gather pipelined by head group")),
                        "l2": "q/k/v/o = 3.1 GB per step >> 126 MB L2, no flush needed"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "aux_kernels": aux,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu

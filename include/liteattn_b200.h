@@ -84,6 +84,21 @@ typedef struct la_combine_params {
   int32_t b, h, s, d;
 } la_combine_params;
 
+/* Caller-side step in front of the attention call, fused: 3-D rotary embedding of Q or K + cast to bf16.
+ * Replaces `rope_apply(x, grid_sizes, freqs)` followed by `.bfloat16()` in the reference's Wan integration
+ * (README.md:301-315; rope_apply is Wan2.1's wan/modules/model.py, restated in oracle/rope.py).   */
+typedef struct la_rope_params {
+  const void* x;           /* (b, s, h, d) fp32 (x_is_bf16 = 0) or bf16 (1), last-dim stride 1, strides in elements */
+  void* out;               /* (b, s, h, d) bf16 contiguous, written */
+  const float* cos_sin;    /* [max_pos, d/2, 2] fp32 (cos, sin): angle of position p for complex pair c; the three
+                            * axes' tables concatenated along d/2 in the order frames | height | width with widths
+                            * d/2 - 2*(d/2/3), d/2/3, d/2/3 (how Wan builds `freqs`) */
+  const int32_t* grid;     /* [b, 3] device int32: (frames, height, width) of each sample; tokens >= f*h*w are cast only */
+  int64_t x_batch_stride, x_row_stride, x_head_stride;
+  int32_t b, s, h, d, max_pos;
+  int32_t x_is_bf16;
+} la_rope_params;
+
 int la_abi_version(void);
 const char* la_last_error(void);
 
@@ -104,6 +119,9 @@ int la_fwd_skip_sm100(const la_fwd_params* fwd, const la_update_params* upd, voi
 
 /* Merge n partial attention results by their LSE. */
 int la_combine_sm100(const la_combine_params* p, void* stream);
+
+/* Fused 3-D RoPE + bf16 cast (HBM-bound elementwise kernel). */
+int la_rope_cast_sm100(const la_rope_params* p, void* stream);
 
 /* Number of kernels launched through this library by the calling process (for bench accounting). */
 uint64_t la_launch_count(void);

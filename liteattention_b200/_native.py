@@ -44,10 +44,18 @@ class CombineParams(ctypes.Structure):
     ]
 
 
+class RopeParams(ctypes.Structure):
+    _fields_ = [
+        ("x", _c_vp), ("out", _c_vp), ("cos_sin", _c_vp), ("grid", _c_vp),
+        ("x_batch_stride", _c_i64), ("x_row_stride", _c_i64), ("x_head_stride", _c_i64),
+        ("b", _c_i32), ("s", _c_i32), ("h", _c_i32), ("d", _c_i32), ("max_pos", _c_i32), ("x_is_bf16", _c_i32),
+    ]
+
+
 _lib = None
 
 EXPORTS = ("la_abi_version", "la_last_error", "la_get_tile_mn", "la_fwd_sm100", "la_skip_update_sm100",
-           "la_fwd_skip_sm100", "la_combine_sm100", "la_launch_count")
+           "la_fwd_skip_sm100", "la_combine_sm100", "la_rope_cast_sm100", "la_launch_count")
 
 
 def lib():
@@ -68,6 +76,7 @@ def lib():
         L.la_skip_update_sm100.argtypes = [ctypes.POINTER(UpdateParams), _c_vp]
         L.la_fwd_skip_sm100.argtypes = [ctypes.POINTER(FwdParams), ctypes.POINTER(UpdateParams), _c_vp]
         L.la_combine_sm100.argtypes = [ctypes.POINTER(CombineParams), _c_vp]
+        L.la_rope_cast_sm100.argtypes = [ctypes.POINTER(RopeParams), _c_vp]
         L.la_watchdog_read.argtypes = [ctypes.POINTER(ctypes.c_uint * 4)]
         if L.la_abi_version() != 1:
             raise RuntimeError("libliteattn_b200.so ABI version mismatch")
@@ -168,3 +177,16 @@ def watchdog_read():
     arr = (ctypes.c_uint * 4)()
     lib().la_watchdog_read(ctypes.byref(arr))
     return list(arr)
+
+
+def rope_cast(x, out, cos_sin, grid):
+    """la_rope_cast_sm100: out (bf16) = rope3d(x) for x fp32 or bf16 (b, s, h, d); cos_sin fp32 [max_pos, d/2, 2];
+    grid int32 [b, 3] on the device."""
+    p = RopeParams()
+    p.x, p.out, p.cos_sin, p.grid = _ptr(x), _ptr(out), _ptr(cos_sin), _ptr(grid)
+    p.x_batch_stride, p.x_row_stride, p.x_head_stride = x.stride(0), x.stride(1), x.stride(2)
+    p.b, p.s, p.h, p.d = x.shape
+    p.max_pos = cos_sin.shape[0]
+    p.x_is_bf16 = int(x.dtype == torch.bfloat16)
+    with torch.cuda.device(x.device):
+        _check(lib().la_rope_cast_sm100(ctypes.byref(p), _stream(x.device)), "la_rope_cast_sm100")

@@ -4,4 +4,5 @@
 #include "la_fwd_sm100.cu"
 #include "la_skip_update.cu"
 #include "la_combine.cu"
+#include "la_rope_cast.cu"
 #include "la_api.cu"

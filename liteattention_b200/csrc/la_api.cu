@@ -104,6 +104,38 @@ int la_get_tile_mn(int head_dim, int element_size, int v_colmajor, int* block_m,
   return (element_size == 2 && head_dim == LA_HEAD_DIM) ? LA_OK : LA_ERR_UNSUPPORTED;
 }
 
+int la_rope_cast_sm100(const la_rope_params* p, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  LA_CHECK_ARG(p != nullptr && p->x && p->out && p->cos_sin && p->grid, "la_rope_cast_sm100: NULL argument");
+  LA_CHECK_ARG(p->b > 0 && p->s > 0 && p->h > 0 && p->d > 0 && p->d % 8 == 0 && p->max_pos > 0,
+               "la_rope_cast_sm100: bad sizes (d must be a multiple of 8)");
+  const int elt = p->x_is_bf16 ? 2 : 4;
+  LA_CHECK_ARG((reinterpret_cast<uintptr_t>(p->x) % 16) == 0 && aligned16(p->out) &&
+                   (p->x_batch_stride * elt) % 16 == 0 && (p->x_row_stride * elt) % 16 == 0 &&
+                   (p->x_head_stride * elt) % 16 == 0,
+               "la_rope_cast_sm100: x / out must be 16-byte aligned with 16-byte aligned strides");
+  la::RopeKernelArgs a;
+  a.x = p->x;
+  a.out = static_cast<__nv_bfloat16*>(p->out);
+  a.cos_sin = reinterpret_cast<const float2*>(p->cos_sin);
+  a.grid = p->grid;
+  a.x_batch_stride = p->x_batch_stride;
+  a.x_row_stride = p->x_row_stride;
+  a.x_head_stride = p->x_head_stride;
+  a.b = p->b; a.s = p->s; a.h = p->h; a.d = p->d; a.max_pos = p->max_pos;
+  LA_CHECK_ARG(p->d / 8 <= la::kRopeThreads, "la_rope_cast_sm100: head_dim too large");
+  const int64_t tokens = (int64_t)p->b * p->s;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int blocks = (int)std::min<int64_t>(tokens, (int64_t)sms * 64);   // a multiple of the SM count, token-stride
+  if (p->x_is_bf16) la::la_rope_cast_kernel<__nv_bfloat16><<<blocks, la::kRopeThreads, 0, stream>>>(a);
+  else la::la_rope_cast_kernel<float><<<blocks, la::kRopeThreads, 0, stream>>>(a);
+  LA_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return LA_OK;
+}
+
 #ifdef LA_PROFILE_CLOCKS
 int la_prof_read(unsigned long long out[32], int reset) {
   LA_CUDA(cudaMemcpyFromSymbol(out, la::g_la_prof, 32 * sizeof(unsigned long long)));

@@ -590,42 +590,68 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       uint64_t acc0 = pack2(0.f, 0.f), acc1 = pack2(0.f, 0.f);
       float mx0 = -INFINITY, mx1 = -INFINITY;
       constexpr int kQuads = kHalfN / 4;   // 22 groups of 4 columns
+#ifndef LA_POST_Q
+#define LA_POST_Q 22                       // quad index at which the half-row max is posted (22 = after the loop)
+#endif
+      constexpr int kPostQ = LA_POST_Q;
+      float m_half = 0.f, m_loc = 0.f;
+      bool ready = false;
+      // The half-row max is complete (the max of the remaining quads is taken ahead of their exponentials), in smem,
+      // and the pair rendezvous + partner read are issued here; the exponentials of the remaining quads follow, so
+      // the exchange latency runs under them instead of after the loop.
+      auto post_and_fetch = [&](int q_from) {
+#pragma unroll
+        for (int qq = q_from; qq < kQuads; ++qq) {
+          mx0 = fmax3(mx0, s[4 * qq], s[4 * qq + 1]);
+          mx1 = fmax3(mx1, s[4 * qq + 2], s[4 * qq + 3]);
+        }
+        m_half = fmaxf(mx0, mx1);
+        sts_f32(xchg_mine, m_half);
+        // Is S(i+1) there yet?  (Asked here so that the answer's latency runs under the verdict.)
+        ready = more && mbar_try_wait(next_bar, next_par);
+        // Exchange the half-row maxima between the two warps that own the same 32 rows.  Passing the barrier also
+        // means the partner has all of its S columns in registers, the condition for our P to land on them.
+        named_bar_sync(pair_bar, 64);
+        m_loc = fmaxf(m_half, lds_f32(xchg_other));
+      };
 #pragma unroll
       for (int q = 0; q < kQuads; ++q) {
         const int j = 4 * q;
-        mx0 = fmax3(mx0, s[j], s[j + 1]);
-        mx1 = fmax3(mx1, s[j + 2], s[j + 3]);
+        if (q == kPostQ) post_and_fetch(q);
+        if (q < kPostQ) {
+          mx0 = fmax3(mx0, s[j], s[j + 1]);
+          mx1 = fmax3(mx1, s[j + 2], s[j + 3]);
+        }
         if (q == kQuads / 2) emit_stat();   // of tile i-1
         float t0, t1, t2, t3, p0, p1, p2, p3;
         unpack2(ffma2(pack2(s[j], s[j + 1]), c2, nm2), t0, t1);
         unpack2(ffma2(pack2(s[j + 2], s[j + 3]), c2, nm2), t2, t3);
         if ((kPolyMask >> ((j >> 1) & 7)) & 1u) {
           exp2_poly_pair(t0, t1, p0, p1);
-        } else {
+        } else if (q < kPostQ) {
           p0 = ex2_approx_ordered(t0);
           p1 = ex2_approx_ordered(t1);
+        } else {
+          p0 = ex2_approx(t0);
+          p1 = ex2_approx(t1);
         }
         if ((kPolyMask >> (((j >> 1) + 1) & 7)) & 1u) {
           exp2_poly_pair(t2, t3, p2, p3);
-        } else {
+        } else if (q < kPostQ) {
           p2 = ex2_approx_ordered(t2);
           p3 = ex2_approx_ordered(t3);
+        } else {
+          p2 = ex2_approx(t2);
+          p3 = ex2_approx(t3);
         }
         acc0 = fadd2(acc0, pack2(p0, p1));   // row sum uses fp32 P, before bf16 rounding (softmax.h:263-273)
         acc1 = fadd2(acc1, pack2(p2, p3));
         pr[j / 2] = pack_bf16(p0, p1);
         pr[j / 2 + 1] = pack_bf16(p2, p3);
       }
-      // Exchange the half-row maxima between the two warps that own the same 32 rows.  Passing the barrier also
-      // means the partner has all of its S columns in registers, the condition for our P to land on them.
-      const float m_half = fmaxf(mx0, mx1);
-      sts_f32(xchg_mine, m_half);
-      // Is S(i+1) there yet?  (Asked here so that the answer's latency runs under the verdict.)
-      const bool ready = more && mbar_try_wait(next_bar, next_par);
+      if (kPostQ >= kQuads) post_and_fetch(kQuads);
       LA_CLK(t2);
       LA_ACC(1, t1, t2);
-      named_bar_sync(pair_bar, 64);
-      float m_loc = fmaxf(m_half, lds_f32(xchg_other));
       // Both warps of the pair see the same m_loc and m_ref for the same rows => the same verdict.
       const bool exact = __any_sync(0xffffffffu, !((m_loc - m_ref) * c <= kLazyTau));
       LA_CLK(t3);

@@ -49,4 +49,15 @@ struct CombineKernelArgs {
 };
 __global__ void la_combine_kernel(const CombineKernelArgs args);
 
+struct RopeKernelArgs {
+  const void* x;            // (b, s, h, d) fp32 or bf16, last dim contiguous, element strides below
+  __nv_bfloat16* out;       // (b, s, h, d) bf16 contiguous
+  const float2* cos_sin;    // [max_pos, d/2] (cos, sin) of the three axes' angles, concatenated along d/2
+  const int32_t* grid;      // [b, 3] (frames, height, width) per sample, device memory
+  int64_t x_batch_stride, x_row_stride, x_head_stride;
+  int32_t b, s, h, d, max_pos;
+};
+template <typename In>
+__global__ void la_rope_cast_kernel(const RopeKernelArgs args);
+
 }  // namespace la

@@ -25,7 +25,7 @@ extern "C" {
 #define LA_ERR_UNSUPPORTED (-2) /* valid for the reference but not built here (e.g. head_dim != 128) */
 #define LA_ERR_CUDA (-3)        /* CUDA driver / runtime error, see la_last_error()                  */
 
-#define LA_ABI_VERSION 1
+#define LA_ABI_VERSION 2   /* 2: la_fwd_params.out_is_f32, la_rope_cast_sm100 */
 
 /* Tile geometry of the skip list.  API-visible: mirrors tile_size_fwd_sm90
  * (hopper/_internal/cpp/tile_size.h:10-62) == LiteAttention.get_MN (hopper/lite_attention.py:87-111).
@@ -59,6 +59,10 @@ typedef struct la_fwd_params {
    * i.e. the left-hand side of the skip predicate (softmax.h:194).  May be NULL. Unvisited entries
    * are left untouched. */
   float* tile_stat;
+  /* 0: out is bf16 (the reference's op).  1: out is fp32 with the same element strides and holds the bf16-rounded
+   * result widened -- exactly what the reference's caller computes with `x = x.float()` after the call
+   * (README.md:312-313), without the extra pass. */
+  int32_t out_is_f32;
 } la_fwd_params;
 
 /* Replaces SkipListWriter + the record/loop logic that the reference fuses into the forward

@@ -24,7 +24,7 @@ class FwdParams(ctypes.Structure):
         [("q", _c_vp), ("k", _c_vp), ("v", _c_vp), ("out", _c_vp), ("lse", _c_vp)]
         + [(f"{t}_{s}_stride", _c_i64) for t in "qkvo" for s in ("batch", "row", "head")]
         + [(n, _c_i32) for n in ("b", "h", "h_k", "seqlen_q", "seqlen_k", "d")]
-        + [("softmax_scale", ctypes.c_float), ("read_list", _c_vp), ("tile_stat", _c_vp)]
+        + [("softmax_scale", ctypes.c_float), ("read_list", _c_vp), ("tile_stat", _c_vp), ("out_is_f32", _c_i32)]
     )
 
 
@@ -78,7 +78,7 @@ def lib():
         L.la_combine_sm100.argtypes = [ctypes.POINTER(CombineParams), _c_vp]
         L.la_rope_cast_sm100.argtypes = [ctypes.POINTER(RopeParams), _c_vp]
         L.la_watchdog_read.argtypes = [ctypes.POINTER(ctypes.c_uint * 4)]
-        if L.la_abi_version() != 1:
+        if L.la_abi_version() != 2:
             raise RuntimeError("libliteattn_b200.so ABI version mismatch")
         _lib = L
     return _lib
@@ -118,6 +118,7 @@ def make_fwd_params(q, k, v, out, lse, softmax_scale, read_list, tile_stat):
     p.softmax_scale = float(softmax_scale)
     p.read_list = _ptr(read_list)
     p.tile_stat = _ptr(tile_stat)
+    p.out_is_f32 = int(out.dtype == torch.float32)
     return p
 
 

@@ -191,7 +191,8 @@ int la_fwd_sm100(const la_fwd_params* p, void* stream_) {
 
   la::FwdKernelArgs a;
   memset(&a, 0, sizeof(a));
-  a.out = static_cast<__nv_bfloat16*>(p->out);
+  a.out = p->out_is_f32 ? nullptr : static_cast<__nv_bfloat16*>(p->out);
+  a.out_f32 = p->out_is_f32 ? static_cast<float*>(p->out) : nullptr;
   a.lse = p->lse;
   a.read_list = p->read_list;
   a.tile_stat = p->tile_stat;

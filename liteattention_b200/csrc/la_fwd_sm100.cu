@@ -720,17 +720,33 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       for (int j = 0; j < 64; ++j) o[j] = 0.f;
     }
     if (q_row < args.seqlen_q) {
-      __nv_bfloat16* optr = args.out + (int64_t)batch * args.o_batch_stride + (int64_t)q_row * args.o_row_stride +
+      const int64_t o_off = (int64_t)batch * args.o_batch_stride + (int64_t)q_row * args.o_row_stride +
                             (int64_t)head * args.o_head_stride + wg * 64;
-      uint4* dst = reinterpret_cast<uint4*>(optr);
+      if (args.out_f32 == nullptr) {
+        uint4* dst = reinterpret_cast<uint4*>(args.out + o_off);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        uint4 v;
-        v.x = pack_bf16(o[8 * j + 0] * inv, o[8 * j + 1] * inv);
-        v.y = pack_bf16(o[8 * j + 2] * inv, o[8 * j + 3] * inv);
-        v.z = pack_bf16(o[8 * j + 4] * inv, o[8 * j + 5] * inv);
-        v.w = pack_bf16(o[8 * j + 6] * inv, o[8 * j + 7] * inv);
-        dst[j] = v;
+        for (int j = 0; j < 8; ++j) {
+          uint4 v;
+          v.x = pack_bf16(o[8 * j + 0] * inv, o[8 * j + 1] * inv);
+          v.y = pack_bf16(o[8 * j + 2] * inv, o[8 * j + 3] * inv);
+          v.z = pack_bf16(o[8 * j + 4] * inv, o[8 * j + 5] * inv);
+          v.w = pack_bf16(o[8 * j + 6] * inv, o[8 * j + 7] * inv);
+          dst[j] = v;
+        }
+      } else {
+        // The consumer's dtype directly: what the reference's caller gets from `x = x.float()`
+        // after the call (README.md:312-313) -- i.e. the bf16-rounded value widened, bit for bit -- without the
+        // extra elementwise pass.
+        float4* dst = reinterpret_cast<float4*>(args.out_f32 + o_off);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float4 v;
+          v.x = __bfloat162float(__float2bfloat16_rn(o[4 * j + 0] * inv));
+          v.y = __bfloat162float(__float2bfloat16_rn(o[4 * j + 1] * inv));
+          v.z = __bfloat162float(__float2bfloat16_rn(o[4 * j + 2] * inv));
+          v.w = __bfloat162float(__float2bfloat16_rn(o[4 * j + 3] * inv));
+          dst[j] = v;
+        }
       }
       if (wg == 0 && args.lse != nullptr)
         args.lse[((int64_t)batch * args.h + head) * args.seqlen_q + q_row] = lse;

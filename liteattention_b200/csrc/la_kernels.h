@@ -13,6 +13,7 @@ constexpr int kFwdSmemBytes = 229632;   // dynamic shared memory of la_fwd_kerne
 
 struct FwdKernelArgs {
   __nv_bfloat16* out;
+  float* out_f32;       // when non-NULL the epilogue writes fp32 here (same element strides) instead of bf16 to out
   float* lse;
   const int32_t* read_list;
   float* tile_stat;
@@ -44,6 +45,7 @@ struct CombineKernelArgs {
   const __nv_bfloat16* o_parts[8];
   const float* lse_parts[8];
   __nv_bfloat16* out;
+  float* out_f32;       // when non-NULL the epilogue writes fp32 here (same element strides) instead of bf16 to out
   float* lse;
   int32_t n_parts, b, h, s, d;
 };

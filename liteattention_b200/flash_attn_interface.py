@@ -134,8 +134,10 @@ def _fwd_cuda(q, k, v, k_new=None, v_new=None, q_v=None, out=None, cu_seqlens_q=
     if out is None:
         out = torch.empty((b, sq, h, d), dtype=q.dtype, device=q.device)                          # :871-875
     else:
-        _check(out.dtype == q.dtype and out.shape == (b, sq, h, d) and out.stride(-1) == 1 and _tma_ok(out),
-               "out must be (batch, seqlen_q, heads, head_dim) bf16 with contiguous, 16-byte aligned rows")
+        # extension: an fp32 `out` receives the bf16-rounded result widened (what the caller's `x.float()` would give)
+        _check(out.dtype in (q.dtype, torch.float32) and out.shape == (b, sq, h, d) and out.stride(-1) == 1 and
+               out.data_ptr() % 16 == 0 and all((s_ * out.element_size()) % 16 == 0 for s_ in out.stride()[:3]),
+               "out must be (batch, seqlen_q, heads, head_dim) bf16 (or fp32) with contiguous, 16-byte aligned rows")
     lse = torch.empty((b, h, sq), dtype=torch.float32, device=q.device)                           # :887-892
 
     qtiles = (sq + _native.BLOCK_M - 1) // _native.BLOCK_M

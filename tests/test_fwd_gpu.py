@@ -326,3 +326,17 @@ def test_back_to_back_launches_in_fresh_processes_do_not_hang(native_lib):
                            timeout=300)
         assert r.returncode == 0 and "SYNC FAILED" not in r.stdout, r.stdout[-500:] + r.stderr[-500:]
         assert "LSE(v1) vs LSE(v2): max 0," in r.stdout, r.stdout[-500:]
+
+
+def test_fp32_output_is_the_bf16_result_widened(native_lib):
+    """out= extension with an fp32 buffer: bit for bit what the reference's caller computes with
+    `x = x.float()` after the call, from the same launch configuration."""
+    from liteattention_b200 import LiteAttention
+    b, s, h = 1, 1500, 3
+    q, k, v = _qkv(b, s, h, seed=11)
+    q, k, v = q.to(DEV), k.to(DEV), v.to(DEV)
+    o_bf = LiteAttention(enable_skipping=True, threshold=-4.0, max_batch_size=b)(q, k, v)
+    buf = torch.full((b, s, h, 128), float("nan"), device=DEV, dtype=torch.float32)
+    o_f32 = LiteAttention(enable_skipping=True, threshold=-4.0, max_batch_size=b)(q, k, v, out=buf)
+    assert o_f32.data_ptr() == buf.data_ptr() and o_f32.dtype == torch.float32
+    assert torch.equal(o_f32, o_bf.float())

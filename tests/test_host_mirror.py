@@ -164,13 +164,14 @@ def test_c_abi_exports_every_declared_symbol(native_lib):
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     declared = set(re.findall(r"\b(la_[a-z0-9_]+)\s*\(", hdr))
     assert {"la_fwd_sm100", "la_skip_update_sm100", "la_fwd_skip_sm100", "la_combine_sm100", "la_get_tile_mn",
-            "la_last_error", "la_abi_version", "la_launch_count"} <= declared
+            "la_rope_cast_sm100", "la_last_error", "la_abi_version", "la_launch_count"} <= declared
     lib = ctypes.CDLL(native_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/liteattn_b200.h but not exported"
-    assert native_lib.lib().la_abi_version() == 1
+    assert native_lib.lib().la_abi_version() == 2
     assert native_lib.get_tile_mn(128) == (128, 176, True)
     assert native_lib.get_tile_mn(64) == (192, 192, False)      # table matches get_MN; kernel not built -> unsupported
     # struct layouts agree with the header (sizes computed by hand from the C declaration)
-    assert ctypes.sizeof(native_lib.FwdParams) == 5 * 8 + 12 * 8 + 6 * 4 + 4 + 4 + 2 * 8
+    assert ctypes.sizeof(native_lib.FwdParams) == 5 * 8 + 12 * 8 + 6 * 4 + 4 + 4 + 2 * 8 + 4 + 4   # + out_is_f32, pad
+    assert ctypes.sizeof(native_lib.RopeParams) == 4 * 8 + 3 * 8 + 6 * 4
     assert ctypes.sizeof(native_lib.UpdateParams) == 4 * 8 + 4 * 4 + 4 + 4 + 8

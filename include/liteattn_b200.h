@@ -63,6 +63,15 @@ typedef struct la_fwd_params {
    * result widened -- exactly what the reference's caller computes with `x = x.float()` after the call
    * (README.md:312-313), without the extra pass. */
   int32_t out_is_f32;
+  /* Sequence-parallel scatter of O (out_rows_per_peer > 0, bf16 only): query row r is written to
+   * out_peer[r / out_rows_per_peer] at row (r % out_rows_per_peer), with the o_*_stride element strides -- the peers'
+   * buffers mapped into this process over NVLink (CUDA IPC / symmetric memory); `out` is ignored.  n_out_peers <= 8
+   * and n_out_peers * out_rows_per_peer >= seqlen_q.  (the return all-to-all of a head-parallel
+   * single-prompt run happens inside the forward's epilogue.) */
+  int32_t n_out_peers;
+  int32_t out_rows_per_peer;
+  int32_t reserved_;
+  void* out_peer[8];
 } la_fwd_params;
 
 /* Replaces SkipListWriter + the record/loop logic that the reference fuses into the forward

@@ -24,7 +24,8 @@ class FwdParams(ctypes.Structure):
         [("q", _c_vp), ("k", _c_vp), ("v", _c_vp), ("out", _c_vp), ("lse", _c_vp)]
         + [(f"{t}_{s}_stride", _c_i64) for t in "qkvo" for s in ("batch", "row", "head")]
         + [(n, _c_i32) for n in ("b", "h", "h_k", "seqlen_q", "seqlen_k", "d")]
-        + [("softmax_scale", ctypes.c_float), ("read_list", _c_vp), ("tile_stat", _c_vp), ("out_is_f32", _c_i32)]
+        + [("softmax_scale", ctypes.c_float), ("read_list", _c_vp), ("tile_stat", _c_vp), ("out_is_f32", _c_i32),
+           ("n_out_peers", _c_i32), ("out_rows_per_peer", _c_i32), ("reserved_", _c_i32), ("out_peer", _c_vp * 8)]
     )
 
 
@@ -106,8 +107,28 @@ def get_tile_mn(head_dim, element_size=2, v_colmajor=False):
     return m.value, n.value, rc == 0
 
 
+class PeerScatter:
+    """Sequence-parallel destination of O: query row r goes to peers[r // rows_per_peer][:, r % rows_per_peer].
+    peers: list of (b, rows_per_peer, heads_here_or_more, d) bf16 views with identical strides (peer memory)."""
+
+    def __init__(self, peers, rows_per_peer):
+        assert 1 <= len(peers) <= 8 and all(t.dtype == torch.bfloat16 and t.stride() == peers[0].stride() for t in peers)
+        self.peers, self.rows_per_peer = list(peers), int(rows_per_peer)
+        self.dtype = torch.bfloat16
+
+    def stride(self, i):
+        return self.peers[0].stride(i)
+
+    def data_ptr(self):
+        return self.peers[0].data_ptr()
+
+
 def make_fwd_params(q, k, v, out, lse, softmax_scale, read_list, tile_stat):
     p = FwdParams()
+    if isinstance(out, PeerScatter):
+        p.n_out_peers, p.out_rows_per_peer = len(out.peers), out.rows_per_peer
+        for i, t in enumerate(out.peers):
+            p.out_peer[i] = t.data_ptr()
     p.q, p.k, p.v, p.out, p.lse = _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse)
     for name, t in (("q", q), ("k", k), ("v", v), ("o", out)):
         setattr(p, f"{name}_batch_stride", t.stride(0))

@@ -193,6 +193,17 @@ int la_fwd_sm100(const la_fwd_params* p, void* stream_) {
   memset(&a, 0, sizeof(a));
   a.out = p->out_is_f32 ? nullptr : static_cast<__nv_bfloat16*>(p->out);
   a.out_f32 = p->out_is_f32 ? static_cast<float*>(p->out) : nullptr;
+  a.rows_per_peer = 0;
+  if (p->out_rows_per_peer > 0) {
+    LA_CHECK_ARG(!p->out_is_f32 && p->n_out_peers >= 1 && p->n_out_peers <= 8 &&
+                     (int64_t)p->n_out_peers * p->out_rows_per_peer >= p->seqlen_q,
+                 "la_fwd_sm100: bad peer scatter (bf16 only, 1..8 peers covering seqlen_q)");
+    for (int i = 0; i < p->n_out_peers; ++i) {
+      LA_CHECK_ARG(p->out_peer[i] != nullptr && aligned16(p->out_peer[i]), "la_fwd_sm100: out_peer[%d] is NULL or unaligned", i);
+      a.out_peer[i] = static_cast<__nv_bfloat16*>(p->out_peer[i]);
+    }
+    a.rows_per_peer = p->out_rows_per_peer;
+  }
   a.lse = p->lse;
   a.read_list = p->read_list;
   a.tile_stat = p->tile_stat;

@@ -722,7 +722,23 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     if (q_row < args.seqlen_q) {
       const int64_t o_off = (int64_t)batch * args.o_batch_stride + (int64_t)q_row * args.o_row_stride +
                             (int64_t)head * args.o_head_stride + wg * 64;
-      if (args.out_f32 == nullptr) {
+      if (args.rows_per_peer > 0) {
+        // Sequence-parallel return path fused into the epilogue: this row belongs to the rank that owns its token.
+        const int dest = q_row / args.rows_per_peer;
+        const int64_t p_off = (int64_t)batch * args.o_batch_stride +
+                              (int64_t)(q_row - dest * args.rows_per_peer) * args.o_row_stride +
+                              (int64_t)head * args.o_head_stride + wg * 64;
+        uint4* dst = reinterpret_cast<uint4*>(args.out_peer[dest] + p_off);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 v;
+          v.x = pack_bf16(o[8 * j + 0] * inv, o[8 * j + 1] * inv);
+          v.y = pack_bf16(o[8 * j + 2] * inv, o[8 * j + 3] * inv);
+          v.z = pack_bf16(o[8 * j + 4] * inv, o[8 * j + 5] * inv);
+          v.w = pack_bf16(o[8 * j + 6] * inv, o[8 * j + 7] * inv);
+          dst[j] = v;
+        }
+      } else if (args.out_f32 == nullptr) {
         uint4* dst = reinterpret_cast<uint4*>(args.out + o_off);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {

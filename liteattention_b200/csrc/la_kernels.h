@@ -14,6 +14,10 @@ constexpr int kFwdSmemBytes = 229632;   // dynamic shared memory of la_fwd_kerne
 struct FwdKernelArgs {
   __nv_bfloat16* out;
   float* out_f32;       // when non-NULL the epilogue writes fp32 here (same element strides) instead of bf16 to out
+  // Sequence-parallel scatter (rows_per_peer > 0): query row r goes to out_peer[r / rows_per_peer] at row
+  // r % rows_per_peer -- peer GPUs' buffers mapped over NVLink; `out` is ignored.
+  __nv_bfloat16* out_peer[8];
+  int32_t rows_per_peer;
   float* lse;
   const int32_t* read_list;
   float* tile_stat;
@@ -46,6 +50,10 @@ struct CombineKernelArgs {
   const float* lse_parts[8];
   __nv_bfloat16* out;
   float* out_f32;       // when non-NULL the epilogue writes fp32 here (same element strides) instead of bf16 to out
+  // Sequence-parallel scatter (rows_per_peer > 0): query row r goes to out_peer[r / rows_per_peer] at row
+  // r % rows_per_peer -- peer GPUs' buffers mapped over NVLink; `out` is ignored.
+  __nv_bfloat16* out_peer[8];
+  int32_t rows_per_peer;
   float* lse;
   int32_t n_parts, b, h, s, d;
 };

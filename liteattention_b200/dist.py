@@ -118,3 +118,60 @@ class BatchParallelLiteAttention:
         if cuda and self.gather:
             torch.cuda.current_stream(q.device).wait_stream(comm)
         return outs, (self._recv if (self.gather and self.rank == self.dst) else None)
+
+
+def ulysses_scatter_heads(x: torch.Tensor, world: int, group=None) -> torch.Tensor:
+    """(B, S_local, H, D) sequence-sharded -> (B, S_local * world, H / world, D) head-sharded (tokens in rank order).
+    One all_to_all_single; works on any backend (gloo in the CPU tests, NCCL over NVLink on GPUs)."""
+    b, sl, h, dd = x.shape
+    hl = h // world
+    send = x.view(b, sl, world, hl, dd).permute(2, 0, 1, 3, 4).contiguous()        # [dst rank, B, S_local, Hl, D]
+    recv = torch.empty_like(send)                                                  # [src rank, B, S_local, Hl, D]
+    dist.all_to_all_single(recv, send, group=group)
+    return recv.permute(1, 0, 2, 3, 4).reshape(b, world * sl, hl, dd)
+
+
+class UlyssesLiteAttention:
+    """Head-parallel attention of ONE prompt across the ranks of `group` (the reference's
+    SeqParallelLiteAttention only keeps one skip state per split, lite_attention.py:322-345, and leaves the data
+    movement to the caller).  Every rank holds S / world tokens of all H heads; the call
+
+        o_local = attn(q_local, k_local, v_local)            # (B, S/world, H, D) -> (B, S/world, H, D)
+
+    (1) re-shards q, k, v to all tokens x H / world heads with one all_to_all each (NCCL over NVLink),
+    (2) runs the QK-Skip forward on this rank's heads (its skip lists cover exactly those heads, never communicated),
+    (3) returns O to sequence sharding INSIDE the forward kernel: the epilogue stores every query row straight into
+        the symmetric-memory output buffer of the rank that owns the token (peer stores over NVLink), followed by one
+        device-side barrier.  There is no return all-to-all kernel.
+    attn_factory() -> a LiteAttention-like callable accepting out= (a PeerScatter)."""
+
+    def __init__(self, attn_factory: Callable[[], Callable], group: Optional[dist.ProcessGroup] = None):
+        self.pg = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.attn = attn_factory()
+        self._symm = self._hdl = self._scatter = None
+
+    def _setup(self, q_local: torch.Tensor):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _native
+        b, sl, h, dd = q_local.shape
+        pg = self.pg if self.pg is not None else dist.group.WORLD
+        self._symm = symm_mem.empty((b, sl, h, dd), dtype=q_local.dtype, device=q_local.device)
+        self._hdl = symm_mem.rendezvous(self._symm, group=pg)
+        hl = h // self.world
+        # peer r's buffer, restricted to the head columns this rank computes
+        peers = [self._hdl.get_buffer(r, (b, sl, h, dd), q_local.dtype)[:, :, self.rank * hl:(self.rank + 1) * hl]
+                 for r in range(self.world)]
+        self._scatter = _native.PeerScatter(peers, rows_per_peer=sl)
+
+    def __call__(self, q_local: torch.Tensor, k_local: torch.Tensor, v_local: torch.Tensor) -> torch.Tensor:
+        b, sl, h, dd = q_local.shape
+        assert h % self.world == 0, "heads must divide evenly over the ranks"
+        if self._hdl is None or self._symm.shape != q_local.shape:
+            self._setup(q_local)
+        q, k, v = (ulysses_scatter_heads(t, self.world, self.pg) for t in (q_local, k_local, v_local))
+        self._hdl.barrier()                 # everyone has consumed the previous step's O before it is overwritten
+        self.attn(q, k, v, out=self._scatter)
+        self._hdl.barrier()                 # every rank's rows have landed here
+        return self._symm

@@ -64,3 +64,29 @@ def test_batch_parallel_gather_world2():
     torch.manual_seed(0)
     q_all = torch.randn(2, 16, 7, 8)
     mp.spawn(_worker, args=(2, _free_port(), q_all), nprocs=2, join=True)
+
+
+def _ulysses_worker(rank, world, port, x_all):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from liteattention_b200.dist import ulysses_scatter_heads
+        b, s, h, d = x_all.shape
+        sl, hl = s // world, h // world
+        mine = x_all[:, rank * sl:(rank + 1) * sl].contiguous()           # sequence shard, all heads
+        got = ulysses_scatter_heads(mine, world)                           # all tokens, my heads
+        assert got.shape == (b, s, hl, d)
+        assert torch.equal(got, x_all[:, :, rank * hl:(rank + 1) * hl])
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_ulysses_head_scatter_layout_world2():
+    """The all_to_all that turns sequence sharding into head sharding (the input side of UlyssesLiteAttention; the
+    output side is the forward kernel's peer-store epilogue, GPU-only: tools/check_ulysses.py, tests/test_dist_gpu.py)."""
+    torch.manual_seed(1)
+    x_all = torch.randn(2, 12, 6, 8)
+    mp.spawn(_ulysses_worker, args=(2, _free_port(), x_all), nprocs=2, join=True)

@@ -172,6 +172,6 @@ def test_c_abi_exports_every_declared_symbol(native_lib):
     assert native_lib.get_tile_mn(128) == (128, 176, True)
     assert native_lib.get_tile_mn(64) == (192, 192, False)      # table matches get_MN; kernel not built -> unsupported
     # struct layouts agree with the header (sizes computed by hand from the C declaration)
-    assert ctypes.sizeof(native_lib.FwdParams) == 5 * 8 + 12 * 8 + 6 * 4 + 4 + 4 + 2 * 8 + 4 + 4   # + out_is_f32, pad
+    assert ctypes.sizeof(native_lib.FwdParams) == 5 * 8 + 12 * 8 + 6 * 4 + 4 + 4 + 2 * 8 + 4 * 4 + 8 * 8   # + out_is_f32, n_out_peers, out_rows_per_peer, reserved, out_peer[8]
     assert ctypes.sizeof(native_lib.RopeParams) == 4 * 8 + 3 * 8 + 6 * 4
     assert ctypes.sizeof(native_lib.UpdateParams) == 4 * 8 + 4 * 4 + 4 + 4 + 8

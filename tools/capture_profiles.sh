@@ -14,4 +14,6 @@ ncu --set full --clock-control none --import-source on -k regex:la_fwd_kernel -s
 ncu --set full --clock-control none --import-source on -k regex:la_fwd_kernel -s 3 -c 1 -o $OUT/prof_fwd_c2_$TAG -f python bench.py --seq 32768 --heads 16 --sparsity 0.5 --steps 2 --warmup 3 --no-e2e --no-cpu > $OUT/prof_fwd_c2_$TAG.log 2>&1
 # skip-list update kernel at the Wan shape
 ncu --set full --clock-control none --import-source on -k regex:la_skip_update_kernel -s 3 -c 1 -o $OUT/prof_upd_wan42_$TAG -f $BENCH > $OUT/prof_upd_wan42_$TAG.log 2>&1
+# fused RoPE + cast kernel (runs inside the bench's aux timing)
+ncu --set full --clock-control none --import-source on -k regex:la_rope_cast -s 3 -c 1 -o $OUT/prof_rope_wan_$TAG -f $BENCH > $OUT/prof_rope_wan_$TAG.log 2>&1
 ls -la $OUT | tail -12

@@ -275,12 +275,14 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + kOffBar + kNumBars * 8);
   volatile int* num_tiles_smem = reinterpret_cast<volatile int*>(smem + kOffBar + kNumBars * 8 + 4);
-  float* xchg = reinterpret_cast<float*>(smem + kOffXchg);
   float* lx = reinterpret_cast<float*>(smem + kOffLx);
   int* stat_s = reinterpret_cast<int*>(smem + kOffStat);
   uint16_t* seq = reinterpret_cast<uint16_t*>(smem + kOffSeq);
   auto bar = [&](uint32_t idx) { return smem_base + kOffBar + idx * 8; };
 
+#ifdef LA_PROFILE_CLOCKS
+  const long long prof_t_entry = clock64();
+#endif
   // ------------------------------------------------------------------ one-time setup
   if (threadIdx.x == 0) {
     mbar_init(bar(kBarQFull), 1);
@@ -553,12 +555,21 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     };
 
     LA_PROF_DECL(7);
+#ifdef LA_PROFILE_CLOCKS
+    long long prof_t_s0 = 0, prof_t_first = 0, prof_t_loop_end = 0;
+#endif
     if (T > 0) {
       // ---------------- first visited tile: always exact (there is no reference yet)
       mbar_wait(bar(kBarSFull + 0), 0, 6, 0);
       tc_fence_after();
+#ifdef LA_PROFILE_CLOCKS
+      prof_t_s0 = clock64();
+#endif
       m_true = exact_tile(0, 0.f);
       publish_p(0);
+#ifdef LA_PROFILE_CLOCKS
+      prof_t_first = clock64();
+#endif
       if (T > 1) {
         mbar_wait(bar(kBarSFull + 1), 0, 6, 1);
         load_s(1);
@@ -694,6 +705,7 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     }
     emit_stat();   // of the last tile
 #ifdef LA_PROFILE_CLOCKS
+    prof_t_loop_end = clock64();
     if (lane == 0 && (warp == 0 || warp == 4)) { LA_PROF_FLUSH(warp == 0 ? 0 : 20, 7); }
 #endif
 
@@ -767,6 +779,16 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       if (wg == 0 && args.lse != nullptr)
         args.lse[((int64_t)batch * args.h + head) * args.seqlen_q + q_row] = lse;
     }
+#ifdef LA_PROFILE_CLOCKS
+    if (warp == 0 && lane == 0 && T > 0) {
+      const long long t_end = clock64();
+      atomicAdd(&g_la_prof[27], (unsigned long long)(prof_t_s0 - prof_t_entry));      // entry -> S(0) ready
+      atomicAdd(&g_la_prof[28], (unsigned long long)(prof_t_first - prof_t_s0));      // first (exact) tile
+      atomicAdd(&g_la_prof[29], (unsigned long long)(t_end - prof_t_loop_end));       // epilogue (O final wait + stores)
+      atomicAdd(&g_la_prof[30], (unsigned long long)(t_end - prof_t_entry));          // whole CTA
+      atomicAdd(&g_la_prof[31], 1ull);
+    }
+#endif
   }
 
   // ------------------------------------------------------------------ teardown

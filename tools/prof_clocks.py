@@ -41,3 +41,9 @@ print(f"   {'total':28s} {tot:8.0f} clk/tile")
 print(" producer")
 for j, nm in enumerate(["wait K empty", "wait V empty"]):
     print(f"   {nm:28s} {v_[16 + j] / max(tiles, 1):8.0f} clk/tile")
+
+if v_[31]:
+    n = v_[31]
+    print(f" per CTA ({n} CTAs, {tiles / n:.1f} tiles each): entry -> S(0) ready {v_[27] / n:.0f} clk, first (exact) tile {v_[28] / n:.0f}, "
+          f"epilogue {v_[29] / n:.0f}, whole CTA {v_[30] / n:.0f} clk  => fixed part ~{(v_[27] + v_[28] + v_[29]) / n:.0f} clk "
+          f"= {(v_[27] + v_[28] + v_[29]) / max(v_[30], 1) * 100:.1f} % of the CTA")

@@ -97,9 +97,8 @@ enum Bar : uint32_t {
   kBarVEmpty = 7,
   kBarSFull = 9,   // +buf
   kBarPFull = 11,  // +buf
-  kBarPvDone = 13,  // one arrival per PV: waited on (phase i-1) only by tiles that rescale O
-  kBarOFull = 14,   // the last PV retired: O is final
-  kNumBars = 15
+  kBarOFull = 13,   // the last PV retired: O is final
+  kNumBars = 14
 };
 
 constexpr uint32_t kTmemCols = 512;
@@ -178,7 +177,8 @@ struct SlowTileArgs {
   uint32_t o_addr;      // this thread's 64 O columns
   uint32_t xchg_mine, xchg_other;  // smem byte addresses of the half-row max exchange slots
   uint32_t bar_id;      // named barrier of the warp pair owning these 32 rows
-  uint32_t bar_pv_done; // mbarrier: PV(i-1) retired
+  uint32_t bar_pv_done; // mbarrier that flips when PV(i-1) retires (the V-empty barrier of its stage) ...
+  uint32_t pv_parity;   // ... and the parity of that phase
   int i;                // visit index of the tile
   int mask_lim;         // < kHalfN: columns >= mask_lim of this half are out of range (first tile only)
   float c;
@@ -236,7 +236,7 @@ __device__ __noinline__ void softmax_slow_tile(SlowTileArgs* a) {
   a->l_run = a->l_run * alpha + (sum0 + sum1);
   if (a->i > 0) {
     // O may only be touched between PV(i-1) retiring and PV(i) being issued.
-    mbar_wait(a->bar_pv_done, (a->i - 1) & 1, 7, a->i);
+    mbar_wait(a->bar_pv_done, a->pv_parity, 7, a->i);
     tc_fence_after();
     if (__any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll 1
@@ -294,7 +294,6 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       mbar_init(bar(kBarSFull + s), 1);
       mbar_init(bar(kBarPFull + s), kSoftmaxThreads / 32);  // one arrival per softmax warp
     }
-    mbar_init(bar(kBarPvDone), 1);
     mbar_init(bar(kBarOFull), 1);
     fence_mbar_init();
   }
@@ -447,10 +446,9 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             umma_ts(tmem_base + kTmemO, p_tmem + j * 8,
                     kDescVHi | (uint64_t)(v_lo + ((s * kKVBytes + j * 16 * 128) >> 4)), kIdescPV, 1);
           }
-          tc_commit(bar(kBarVEmpty + s));
-          tc_commit(bar(kBarPvDone));
-          // Not kBarPvDone: a parity wait is only meaningful one phase behind, and the speculative tiles never
-          // wait on it, so by the epilogue that barrier may be two phases ahead of a warp's last wait.
+          tc_commit(bar(kBarVEmpty + s));   // V stage reusable; also "PV(i) retired" for a tile that must rescale O
+          // O-final gets its own barrier: a parity wait is only meaningful one phase behind, and a softmax warp may
+          // not have waited on V-empty for many tiles by the time it reaches the epilogue.
           if (i == Tu - 1) tc_commit(bar(kBarOFull));
         }
         __syncwarp();
@@ -532,7 +530,11 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       a.xchg_mine = xchg_base + (buf * kSoftmaxThreads + tid) * 4;
       a.xchg_other = xchg_base + (buf * kSoftmaxThreads + (tid ^ 128)) * 4;
       a.bar_id = pair_bar;
-      a.bar_pv_done = bar(kBarPvDone);
+      // PV(i-1) retiring is what frees V stage (i-1)&1: phase ((i-1)>>1) of that stage's empty barrier.  When tile i
+      // is being processed PV(i-2) has retired (S(i) was committed after it) and PV(i+1) cannot have been issued, so
+      // the barrier is at most one phase away from the one waited for and the parity test is unambiguous.
+      a.bar_pv_done = bar(kBarVEmpty + ((i - 1) & 1));
+      a.pv_parity = (uint32_t)(((i - 1) >> 1) & 1);
       a.i = i;
       // Key columns >= seqlen_k are masked in the FIRST processed tile only (mask.h:66-76, mainloop :1626).
       a.mask_lim = (i == 0) ? args.seqlen_k - (seq[0] * kN + wg * kHalfN) : kHalfN;

@@ -29,7 +29,7 @@
 //       - the verdict (does any row max run ahead of m_ref by more than 8?) needs the full-row max: the two warps
 //         that own a row exchange half-row maxima through smem and a pair of split named barriers.  If it fails,
 //         the tile is redone exactly, out of line (softmax_slow_tile): m_ref := true max, l and O rescaled.
-//       - every other column pair takes its exp2 on the FMA pipe (Cody-Waite + cubic), which balances the MUFU
+//       - 2 of every 8 column pairs (staggered between the two column halves) take their exp2 on the FMA pipe (Cody-Waite + cubic), which balances the MUFU
 //         pipe against instruction dispatch; S(i+1) is pulled from TMEM while P(i) is being published; the
 //         statistic of tile i is reduced inside tile i+1's exponential loop.
 //
@@ -38,6 +38,8 @@
 // 75-80 B/clk/SM against the 64 needed (tools/l2_rate.cu); the softmax chain S(i) -> P(i) is ~2000 clk, and with
 // only two S buffers PV(i) -> QK(i+2) cannot be decoupled from it.  See DESIGN.md section 3.1.
 #include <cuda_bf16.h>
+
+#include <type_traits>
 
 #include "la_kernels.h"
 #include "la_ptx.cuh"
@@ -138,9 +140,14 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // MUFU.EX2 runs at 16/clk/SM: 128x176 exponentials take exactly as long as the tile's two MMAs (1408 clk), so a
 // share of them has to come off the MUFU pipe for the softmax to fit under the tensor pipe at all.
 #ifndef LA_POLY_MASK
-#define LA_POLY_MASK 0x55u   // every other column pair; chosen by same-box A/B (tools/build_variants.py + tools/sustained.py)
+#define LA_POLY_MASK 0x11u   // pairs 0 and 4 of every 8 for the first column half ...
 #endif
 constexpr uint32_t kPolyMask = LA_POLY_MASK;
+#ifndef LA_POLY_MASK_B
+#define LA_POLY_MASK_B 0x44u  // ... pairs 2 and 6 for the second: the two warps of a sub-partition run in near lock-step,
+                              // staggering their FMA-pipe pairs is worth 2 % (same-box A/B, tools/build_variants.py)
+#endif
+constexpr uint32_t kPolyMaskB = LA_POLY_MASK_B;
 
 // The scaling reference m_ref of a row trails its true running max by at most kLazyTau (log2 units): P <= 2^tau.
 // While the true max stays within tau of m_ref, P(i) does not depend on tile i's own max, so the exponentials
@@ -627,6 +634,10 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         named_bar_sync(pair_bar, 64);
         m_loc = fmaxf(m_half, lds_f32(xchg_other));
       };
+      // The two warps that share a sub-partition run this loop in near lock-step; each column half has its own mask so
+      // that their FMA-pipe pairs do not coincide.
+      auto exp_loop = [&](auto mask_tag) {
+        constexpr uint32_t kMask = decltype(mask_tag)::value;
 #pragma unroll
       for (int q = 0; q < kQuads; ++q) {
         const int j = 4 * q;
@@ -639,7 +650,7 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         float t0, t1, t2, t3, p0, p1, p2, p3;
         unpack2(ffma2(pack2(s[j], s[j + 1]), c2, nm2), t0, t1);
         unpack2(ffma2(pack2(s[j + 2], s[j + 3]), c2, nm2), t2, t3);
-        if ((kPolyMask >> ((j >> 1) & 7)) & 1u) {
+        if ((kMask >> ((j >> 1) & 7)) & 1u) {
           exp2_poly_pair(t0, t1, p0, p1);
         } else if (q < kPostQ) {
           p0 = ex2_approx_ordered(t0);
@@ -648,7 +659,7 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           p0 = ex2_approx(t0);
           p1 = ex2_approx(t1);
         }
-        if ((kPolyMask >> (((j >> 1) + 1) & 7)) & 1u) {
+        if ((kMask >> (((j >> 1) + 1) & 7)) & 1u) {
           exp2_poly_pair(t2, t3, p2, p3);
         } else if (q < kPostQ) {
           p2 = ex2_approx_ordered(t2);
@@ -662,6 +673,9 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         pr[j / 2] = pack_bf16(p0, p1);
         pr[j / 2 + 1] = pack_bf16(p2, p3);
       }
+      };
+      if (kPolyMaskB == kPolyMask || wg == 0) exp_loop(std::integral_constant<uint32_t, kPolyMask>{});
+      else exp_loop(std::integral_constant<uint32_t, kPolyMaskB>{});
       if (kPostQ >= kQuads) post_and_fetch(kQuads);
       LA_CLK(t2);
       LA_ACC(1, t1, t2);

@@ -616,6 +616,12 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 #define LA_POST_Q 22                       // quad index at which the half-row max is posted (22 = after the loop)
 #endif
       constexpr int kPostQ = LA_POST_Q;
+#ifndef LA_STAT_Q
+#define LA_STAT_Q 11                       // quad at which the previous tile's statistic is reduced
+#endif
+#ifndef LA_EX2_ORDERED
+#define LA_EX2_ORDERED 1                   // 1: MUFU statements pinned in program order (volatile asm)
+#endif
       float m_half = 0.f, m_loc = 0.f;
       bool ready = false;
       // The half-row max is complete (the max of the remaining quads is taken ahead of their exponentials), in smem,
@@ -648,13 +654,13 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           mx0 = fmax3(mx0, s[j], s[j + 1]);
           mx1 = fmax3(mx1, s[j + 2], s[j + 3]);
         }
-        if (q == kQuads / 2) emit_stat();   // of tile i-1
+        if (q == LA_STAT_Q) emit_stat();   // of tile i-1
         float t0, t1, t2, t3, p0, p1, p2, p3;
         unpack2(ffma2(pack2(s[j], s[j + 1]), c2, nm2), t0, t1);
         unpack2(ffma2(pack2(s[j + 2], s[j + 3]), c2, nm2), t2, t3);
         if ((kMask >> ((j >> 1) & 7)) & 1u) {
           exp2_poly_pair(t0, t1, p0, p1);
-        } else if (q < kPostQ) {
+        } else if (q < kPostQ && LA_EX2_ORDERED) {
           p0 = ex2_approx_ordered(t0);
           p1 = ex2_approx_ordered(t1);
         } else {
@@ -663,7 +669,7 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         }
         if ((kMask >> (((j >> 1) + 1) & 7)) & 1u) {
           exp2_poly_pair(t2, t3, p2, p3);
-        } else if (q < kPostQ) {
+        } else if (q < kPostQ && LA_EX2_ORDERED) {
           p2 = ex2_approx_ordered(t2);
           p3 = ex2_approx_ordered(t3);
         } else {

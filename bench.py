@@ -378,7 +378,7 @@ def main():
                                    "update" + ("" if world == 1 else f"; batch-parallel, O gathered to rank 0 over NCCL "
                                                                       f"in {n_groups} head groups"),
                        "batch_per_gpu": B, "seq_len": S, "heads": H, "head_dim": D, "sparsity": step_sparsity,
-                       "parallelism": f"batch-parallel x{world}" + ("" if world == 1 else (", O stored by the forward epilogue into rank 0's symmetric buffer over NVLink (fused gather)" if args.gather == "peer" else ", NCCL gather pipelined by head group")),
+                       "parallelism": f"batch-parallel x{world}" + ("" if world == 1 else (", O stored by the forward epilogue into rank 0's symmetric buffer over NVLink (fused gather)" if bp.peer_store else ", NCCL gather" + ("" if args.gather == "nccl" else " (peer-store setup failed: " + str(bp.fallback_reason) + ")"))),
                        "l2": "q/k/v/o = 3.1 GB per step >> 126 MB L2, no flush needed"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "aux_kernels": aux,
         }

@@ -55,6 +55,7 @@ class BatchParallelLiteAttention:
         if self.peer_store:
             num_groups = 1                      # nothing to overlap: the epilogue IS the transfer
         self._symm = self._hdl = self._peer_slot = None
+        self.fallback_reason = None
         self.groups = head_groups(num_heads, num_groups)
         self.attn = [attn_factory() for _ in self.groups]
         self.dst = dst
@@ -84,9 +85,15 @@ class BatchParallelLiteAttention:
         gathered) where `gathered` is, on `dst`, a list over head groups of lists over ranks of
         (B_local, S, Hg, D) tensors (None elsewhere / when not gathering).  With peer_store the first element is
         [this rank's slot of the destination buffer] and `gathered` is [[slot 0, slot 1, ...]] on `dst`."""
-        if self.peer_store:
-            if self._hdl is None:
+        if self.peer_store and self._hdl is None:
+            try:
                 self._setup_peer(q)
+            except Exception as e:  # noqa: BLE001 -- no symmetric memory / no P2P on this box: NCCL gather instead
+                import warnings
+                warnings.warn(f"BatchParallelLiteAttention: peer-store gather unavailable ({e}); using the NCCL gather")
+                self.peer_store = False
+                self.fallback_reason = str(e)[:200]
+        if self.peer_store:
             o = self.attn[0](q, k, v, out=self._peer_slot)
             self._hdl.barrier()        # device-side, stream-ordered: every rank's stores have landed at dst
             gathered = [[self._symm[r] for r in range(self.world)]] if self.rank == self.dst else None

@@ -624,9 +624,10 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 #endif
       float m_half = 0.f, m_loc = 0.f;
       bool ready = false;
-      // The half-row max is complete (the max of the remaining quads is taken ahead of their exponentials), in smem,
-      // and the pair rendezvous + partner read are issued here; the exponentials of the remaining quads follow, so
-      // the exchange latency runs under them instead of after the loop.
+      // Tuning knobs kept from the same-box sweeps (tools/build_variants.py + tools/sustained.py): posting the half-row
+      // max before the last quads (LA_POST_Q < 22: the max of the remaining quads is taken ahead of their exponentials
+      // so that the exchange runs under them), where the statistic is reduced, and whether the MUFU statements are
+      // pinned in program order, all measured within +-1 % of each other; the defaults are the best of that sweep.
       auto post_and_fetch = [&](int q_from) {
 #pragma unroll
         for (int qq = q_from; qq < kQuads; ++qq) {

@@ -25,7 +25,7 @@ extern "C" {
 #define LA_ERR_UNSUPPORTED (-2) /* valid for the reference but not built here (e.g. head_dim != 128) */
 #define LA_ERR_CUDA (-3)        /* CUDA driver / runtime error, see la_last_error()                  */
 
-#define LA_ABI_VERSION 2   /* 2: la_fwd_params.out_is_f32, la_rope_cast_sm100 */
+#define LA_ABI_VERSION 3   /* 2: la_fwd_params.out_is_f32, la_rope_cast_sm100; 3: la_combine_params dtypes, la_fwd_params.sched */
 
 /* Tile geometry of the skip list.  API-visible: mirrors tile_size_fwd_sm90
  * (hopper/_internal/cpp/tile_size.h:10-62) == LiteAttention.get_MN (hopper/lite_attention.py:87-111).
@@ -86,15 +86,18 @@ typedef struct la_update_params {
   int32_t* overflow_count;     /* optional device counter: rows whose new list would not fit   */
 } la_update_params;
 
-/* O_i/LSE_i partial-attention merge (reference analogue: flash_fwd_combine_kernel.h, disabled in the
- * shipped build; README.md:222-250 asks callers to do this themselves). */
+/* O_i/LSE_i partial-attention merge.  Replaces the reference op lite_attention::fwd_combine = mha_combine
+ * (hopper/_internal/cpp/flash_api.cpp:1620-1720, kernel flash_fwd_combine_kernel.h -- compiled out of the shipped
+ * build, hopper/setup.py:48; README.md:222-250 asks callers to merge partial results by LSE themselves). */
 typedef struct la_combine_params {
-  const void* const* o_parts;    /* HOST array of n_parts device pointers, each (b, s, h, d) bf16 contiguous */
+  const void* const* o_parts;    /* HOST array of n_parts device pointers, each (b, s, h, d) contiguous, bf16 or fp32 */
   const float* const* lse_parts; /* HOST array of n_parts device pointers, each (b, h, s) fp32 contiguous    */
   int32_t n_parts;
-  void* out;                     /* (b, s, h, d) bf16 contiguous */
+  void* out;                     /* (b, s, h, d) contiguous, bf16 or fp32 */
   float* lse;                    /* (b, h, s) fp32, may be NULL  */
   int32_t b, h, s, d;
+  int32_t parts_are_f32;         /* 0: bf16 partials (what la_fwd_sm100 writes), 1: fp32 (the reference op's contract) */
+  int32_t out_is_f32;            /* 0: bf16 result, 1: fp32 */
 } la_combine_params;
 
 /* Caller-side step in front of the attention call, fused: 3-D rotary embedding of Q or K + cast to bf16.

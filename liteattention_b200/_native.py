@@ -42,6 +42,7 @@ class CombineParams(ctypes.Structure):
         ("o_parts", ctypes.POINTER(_c_vp)), ("lse_parts", ctypes.POINTER(_c_vp)), ("n_parts", _c_i32),
         ("out", _c_vp), ("lse", _c_vp),
         ("b", _c_i32), ("h", _c_i32), ("s", _c_i32), ("d", _c_i32),
+        ("parts_are_f32", _c_i32), ("out_is_f32", _c_i32),
     ]
 
 
@@ -79,7 +80,7 @@ def lib():
         L.la_combine_sm100.argtypes = [ctypes.POINTER(CombineParams), _c_vp]
         L.la_rope_cast_sm100.argtypes = [ctypes.POINTER(RopeParams), _c_vp]
         L.la_watchdog_read.argtypes = [ctypes.POINTER(ctypes.c_uint * 4)]
-        if L.la_abi_version() != 2:
+        if L.la_abi_version() != 3:
             raise RuntimeError("libliteattn_b200.so ABI version mismatch")
         _lib = L
     return _lib
@@ -187,6 +188,8 @@ def combine(o_parts, lse_parts, out, lse):
     c.o_parts, c.lse_parts, c.n_parts = oa, la, n
     c.out, c.lse = _ptr(out), _ptr(lse)
     c.b, c.h, c.s, c.d = b, h, s, d
+    c.parts_are_f32 = int(o_parts[0].dtype == torch.float32)
+    c.out_is_f32 = int(out.dtype == torch.float32)
     with torch.cuda.device(out.device):
         _check(lib().la_combine_sm100(ctypes.byref(c), _stream(out.device)), "la_combine_sm100")
 

@@ -219,10 +219,13 @@ int la_fwd_sm100(const la_fwd_params* p, void* stream_) {
   a.softmax_scale = p->softmax_scale;
   a.scale_log2 = p->softmax_scale * (float)M_LOG2E;  // mainloop :760
 
-  static bool attr_set = false;  // per process; the attribute is per function per device, cheap to repeat
-  if (!attr_set) {
+  // The attribute is per function per DEVICE: remember it per device ordinal (a process may drive several GPUs).
+  static std::atomic<bool> attr_set[64];
+  int dev = 0;
+  LA_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev].load(std::memory_order_acquire)) {
     LA_CUDA(cudaFuncSetAttribute(la::la_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, la::kFwdSmemBytes));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev].store(true, std::memory_order_release);
   }
   dim3 grid(qtiles, p->h, p->b);
   la::la_fwd_kernel<<<grid, la::kFwdThreads, la::kFwdSmemBytes, stream>>>(tq, tk, tv, a);
@@ -279,11 +282,11 @@ int la_combine_sm100(const la_combine_params* p, void* stream_) {
   memset(&a, 0, sizeof(a));
   for (int i = 0; i < p->n_parts; ++i) {
     LA_CHECK_ARG(p->o_parts[i] && p->lse_parts[i] && aligned16(p->o_parts[i]), "la_combine_sm100: bad part %d", i);
-    a.o_parts[i] = static_cast<const __nv_bfloat16*>(p->o_parts[i]);
+    a.o_parts[i] = p->o_parts[i];
     a.lse_parts[i] = p->lse_parts[i];
   }
   LA_CHECK_ARG(aligned16(p->out), "la_combine_sm100: out must be 16-byte aligned");
-  a.out = static_cast<__nv_bfloat16*>(p->out);
+  a.out = p->out;
   a.lse = p->lse;
   a.n_parts = p->n_parts;
   a.b = p->b;
@@ -292,7 +295,13 @@ int la_combine_sm100(const la_combine_params* p, void* stream_) {
   a.d = p->d;
   const int64_t total = (int64_t)p->b * p->s * p->h * (p->d / 8);
   int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
-  la::la_combine_kernel<<<blocks, 256, 0, stream>>>(a);
+  if (p->parts_are_f32) {
+    if (p->out_is_f32) la::la_combine_kernel<float, float><<<blocks, 256, 0, stream>>>(a);
+    else la::la_combine_kernel<float, __nv_bfloat16><<<blocks, 256, 0, stream>>>(a);
+  } else {
+    if (p->out_is_f32) la::la_combine_kernel<__nv_bfloat16, float><<<blocks, 256, 0, stream>>>(a);
+    else la::la_combine_kernel<__nv_bfloat16, __nv_bfloat16><<<blocks, 256, 0, stream>>>(a);
+  }
   LA_CUDA(cudaGetLastError());
   g_launches.fetch_add(1);
   return LA_OK;

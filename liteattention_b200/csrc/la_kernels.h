@@ -46,17 +46,13 @@ __global__ void la_skip_update_kernel(const UpdateKernelArgs args);
 size_t la_skip_update_smem_bytes(int ktiles);
 
 struct CombineKernelArgs {
-  const __nv_bfloat16* o_parts[8];
-  const float* lse_parts[8];
-  __nv_bfloat16* out;
-  float* out_f32;       // when non-NULL the epilogue writes fp32 here (same element strides) instead of bf16 to out
-  // Sequence-parallel scatter (rows_per_peer > 0): query row r goes to out_peer[r / rows_per_peer] at row
-  // r % rows_per_peer -- peer GPUs' buffers mapped over NVLink; `out` is ignored.
-  __nv_bfloat16* out_peer[8];
-  int32_t rows_per_peer;
+  const void* o_parts[8];      // (b, s, h, d) contiguous, bf16 or fp32 (template parameter In)
+  const float* lse_parts[8];   // (b, h, s) fp32 contiguous
+  void* out;                   // (b, s, h, d) contiguous, bf16 or fp32 (template parameter Out)
   float* lse;
   int32_t n_parts, b, h, s, d;
 };
+template <typename In, typename Out>
 __global__ void la_combine_kernel(const CombineKernelArgs args);
 
 struct RopeKernelArgs {

@@ -94,6 +94,10 @@ class BatchParallelLiteAttention:
                 self.peer_store = False
                 self.fallback_reason = str(e)[:200]
         if self.peer_store:
+            # `gathered` from the previous call are views of the destination's symmetric buffer: nobody may store into
+            # it until the destination's stream has passed its reads of step N-1 (write-after-read across ranks).
+            # The result of a call is therefore valid until the next call on ANY rank reaches this barrier.
+            self._hdl.barrier()
             o = self.attn[0](q, k, v, out=self._peer_slot)
             self._hdl.barrier()        # device-side, stream-ordered: every rank's stores have landed at dst
             gathered = [[self._symm[r] for r in range(self.world)]] if self.rank == self.dst else None

@@ -14,7 +14,8 @@ import torch
 
 from . import _native
 
-__all__ = ["flash_attn_func", "flash_attn_combine", "FlashAttnFunc", "_flash_attn_forward", "maybe_contiguous"]
+__all__ = ["flash_attn_func", "flash_attn_combine", "FlashAttnFunc", "_flash_attn_forward", "maybe_contiguous",
+           "fwd_peer_scatter"]
 
 _FWD_SCHEMA = (
     "fwd("
@@ -58,11 +59,69 @@ _FWD_SCHEMA = (
     "float thr = -3.0) -> (Tensor(out!), Tensor, Tensor, Tensor)"
 )
 
-# Ops the reference registers but cannot reach from LiteAttention (bwd throws there too, flash_api.cpp:1251-1254).
-_STUB_SCHEMAS = {
-    "bwd": "bwd(Tensor dout, Tensor q, Tensor k, Tensor v, Tensor out, Tensor softmax_lse) -> Tensor[]",
-    "get_scheduler_metadata": "get_scheduler_metadata(int batch_size, int max_seqlen_q, int max_seqlen_k) -> Tensor",
-}
+# Ops the reference registers next to fwd (flash_api.cpp:1764-1816), schema strings identical.  bwd throws in the
+# reference's shipped build too (:1251-1254, DISABLE_BACKWARD); get_scheduler_metadata only serves the varlen /
+# split schedulers that are compiled out.  fwd_combine is implemented (la_combine_sm100).
+_BWD_SCHEMA = (
+    "bwd("
+    "Tensor dout,"
+    "Tensor q,"
+    "Tensor k,"
+    "Tensor v,"
+    "Tensor out,"
+    "Tensor softmax_lse,"
+    "Tensor(dq!)? dq = None,"
+    "Tensor(dk!)? dk = None,"
+    "Tensor(dv!)? dv = None,"
+    "Tensor? cu_seqlens_q = None,"
+    "Tensor? cu_seqlens_k = None,"
+    "Tensor? seqused_q = None,"
+    "Tensor? seqused_k = None,"
+    "int? max_seqlen_q = None,"
+    "int? max_seqlen_k = None,"
+    "float? softmax_scale = None,"
+    "bool is_causal = False,"
+    "int window_size_left = -1,"
+    "int window_size_right = -1,"
+    "float softcap = 0.0,"
+    "bool deterministic = False,"
+    "int sm_margin = 0) -> (Tensor(dq!), Tensor(dk!), Tensor(dv!), Tensor, Tensor, Tensor, Tensor, Tensor)"
+)
+_COMBINE_SCHEMA = (
+    "fwd_combine("
+    "Tensor out_partial,"
+    "Tensor lse_partial,"
+    "Tensor(out!)? out = None,"
+    "ScalarType? out_dtype = None) -> (Tensor(out!), Tensor)"
+)
+_SCHED_SCHEMA = (
+    "get_scheduler_metadata("
+    "int batch_size,"
+    "int max_seqlen_q,"
+    "int max_seqlen_k,"
+    "int num_heads,"
+    "int num_heads_k,"
+    "int headdim,"
+    "int headdim_v,"
+    "ScalarType qkv_dtype,"
+    "Tensor seqused_k,"
+    "Tensor? cu_seqlens_q = None,"
+    "Tensor? cu_seqlens_k = None,"
+    "Tensor? cu_seqlens_k_new = None,"
+    "Tensor? seqused_q = None,"
+    "Tensor? leftpad_k = None,"
+    "int? page_size = None,"
+    "int max_seqlen_k_new = 0,"
+    "bool is_causal = False,"
+    "int window_size_left = -1,"
+    "int window_size_right = -1,"
+    "int attention_chunk = 0,"
+    "bool has_softcap = False,"
+    "int num_splits = 0,"
+    "bool? pack_gqa = None,"
+    "int sm_margin = 0) -> Tensor"
+)
+_STUB_SCHEMAS = {"bwd": _BWD_SCHEMA, "get_scheduler_metadata": _SCHED_SCHEMA}
 
 
 def _check(cond, msg):
@@ -106,7 +165,27 @@ def _fwd_cuda(q, k, v, k_new=None, v_new=None, q_v=None, out=None, cu_seqlens_q=
     if num_splits > 1:
         raise NotImplementedError("lite_attention::fwd (sm_100a): num_splits > 1 is not supported")
 
+    q, k, v, softmax_scale = _validate_qkv(q, k, v, softmax_scale)
+    b, sq, h, d = q.shape
+    if out is None:
+        out = torch.empty((b, sq, h, d), dtype=q.dtype, device=q.device)                          # :871-875
+    else:
+        # extension: an fp32 `out` receives the bf16-rounded result widened (what the caller's `x.float()` would give)
+        _check(out.dtype in (q.dtype, torch.float32) and out.shape == (b, sq, h, d) and out.stride(-1) == 1 and
+               out.device == q.device and
+               out.data_ptr() % 16 == 0 and all((s_ * out.element_size()) % 16 == 0 for s_ in out.stride()[:3]),
+               "out must be (batch, seqlen_q, heads, head_dim) bf16 (or fp32) on q's device with contiguous, "
+               "16-byte aligned rows")
+    lse = _launch_fwd(q, k, v, out, softmax_scale, attn_read_list, attn_must_do_list, attn_write_list, thr)
+    empty = q.new_empty(0)
+    return out, lse, empty, empty.float()
+
+
+def _validate_qkv(q, k, v, softmax_scale):
+    """The tensor checks of mha_fwd (flash_api.cpp:700-856) for the one configuration built here; returns q, k, v made
+    TMA-addressable (16-byte aligned base, strides multiples of 8 elements) and the default scale."""
     _check(q.is_cuda and k.is_cuda and v.is_cuda, "q, k, v must be CUDA tensors")
+    _check(q.device == k.device and q.device == v.device, "q, k, v must be on the same device")
     _check(q.dtype == torch.bfloat16, "lite_attention::fwd (sm_100a) only supports bf16")        # setup.py:54-55
     _check(k.dtype == q.dtype and v.dtype == q.dtype, "query, key and value must have the same dtype")
     _check(q.dim() == 4 and k.dim() == 4 and v.dim() == 4, "q, k, v must be (batch, seqlen, heads, head_dim)")
@@ -124,22 +203,31 @@ def _fwd_cuda(q, k, v, k_new=None, v_new=None, q_v=None, out=None, cu_seqlens_q=
 
     def _tma_ok(t):
         return t.data_ptr() % 16 == 0 and all(s % 8 == 0 for s in t.stride()[:3])
-    if not _tma_ok(q):
-        q = q.contiguous()
-    if not _tma_ok(k):
-        k = k.contiguous()
-    if not _tma_ok(v):
-        v = v.contiguous()
+    q, k, v = (t if _tma_ok(t) else t.contiguous() for t in (q, k, v))
+    return q, k, v, softmax_scale
 
-    if out is None:
-        out = torch.empty((b, sq, h, d), dtype=q.dtype, device=q.device)                          # :871-875
-    else:
-        # extension: an fp32 `out` receives the bf16-rounded result widened (what the caller's `x.float()` would give)
-        _check(out.dtype in (q.dtype, torch.float32) and out.shape == (b, sq, h, d) and out.stride(-1) == 1 and
-               out.data_ptr() % 16 == 0 and all((s_ * out.element_size()) % 16 == 0 for s_ in out.stride()[:3]),
-               "out must be (batch, seqlen_q, heads, head_dim) bf16 (or fp32) with contiguous, 16-byte aligned rows")
+
+# Scratch for the per-tile statistic (forward writes it, the update kernel reads it, same stream, same call): one
+# buffer per (device, stream, shape) shared by every layer object instead of a 40 MB torch.empty per call.
+_STAT_WS = {}
+
+
+def _stat_workspace(device, shape):
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, tuple(shape))
+    ws = _STAT_WS.get(key)
+    if ws is None:
+        if len(_STAT_WS) >= 16:
+            _STAT_WS.clear()
+        ws = _STAT_WS[key] = torch.empty(shape, dtype=torch.float32, device=device)
+    return ws
+
+
+def _launch_fwd(q, k, v, out, softmax_scale, attn_read_list, attn_must_do_list, attn_write_list, thr):
+    """List validation (flash_api.cpp:915-963 + geometry) and the C-ABI call; `out` is a tensor or a
+    _native.PeerScatter.  q, k, v must have been through _validate_qkv.  Returns softmax_lse."""
+    b, sq, h, d = q.shape
+    sk = k.shape[1]
     lse = torch.empty((b, h, sq), dtype=torch.float32, device=q.device)                           # :887-892
-
     qtiles = (sq + _native.BLOCK_M - 1) // _native.BLOCK_M
     ktiles = (sk + _native.BLOCK_N - 1) // _native.BLOCK_N
     if attn_read_list is not None:                       # is_skipable (flash_api.cpp:919-936)
@@ -150,21 +238,68 @@ def _fwd_cuda(q, k, v, k_new=None, v_new=None, q_v=None, out=None, cu_seqlens_q=
             _check_list(attn_write_list, "attn_write_list", b, h, qtiles, ktiles, q.device)
             _check(attn_write_list.data_ptr() != attn_read_list.data_ptr(),
                    "attn_read_list and attn_write_list must not alias")
-            stat = torch.empty((b, h, qtiles, ktiles), dtype=torch.float32, device=q.device)
+            stat = _stat_workspace(q.device, (b, h, qtiles, ktiles))
             _native.fwd_skip(q, k, v, out, lse, softmax_scale, attn_read_list, attn_must_do_list,
                              attn_write_list, stat, thr)
         else:
             _native.fwd(q, k, v, out, lse, softmax_scale, attn_read_list, None)
     else:
         _native.fwd(q, k, v, out, lse, softmax_scale, None, None)
-    empty = q.new_empty(0)
-    return out, lse, empty, empty.float()
+    return lse
+
+
+def fwd_peer_scatter(q, k, v, scatter, softmax_scale=None, attn_read_list=None, attn_must_do_list=None,
+                     attn_write_list=None, thr=-3.0):
+    """The forward with O scattered by rows to peer GPUs (liteattention_b200/dist.py).  Not expressible through the
+    reference's op (its `out` is one tensor); same validation as the op, then the C ABI.  Returns softmax_lse."""
+    q, k, v, softmax_scale = _validate_qkv(q, k, v, softmax_scale)
+    b, sq, h, d = q.shape
+    _check(isinstance(scatter, _native.PeerScatter), "scatter must be a PeerScatter")
+    p0 = scatter.peers[0]
+    _check(all(t.device.type == "cuda" and t.dim() == 4 and t.shape[0] >= b and t.shape[2] == h and t.shape[3] == d
+               and t.stride(-1) == 1 and t.shape[1] >= min(scatter.rows_per_peer, sq) for t in scatter.peers)
+           and scatter.rows_per_peer * len(scatter.peers) >= sq and p0.data_ptr() % 16 == 0
+           and all(s_ % 8 == 0 for s_ in p0.stride()[:3]),
+           "PeerScatter buffers must be (batch, rows_per_peer, heads, head_dim) bf16 views covering seqlen_q")
+    return _launch_fwd(q, k, v, scatter, softmax_scale, attn_read_list, attn_must_do_list, attn_write_list, thr)
+
+
+def _fwd_combine_cuda(out_partial, lse_partial, out=None, out_dtype=None):
+    """lite_attention::fwd_combine = mha_combine (flash_api.cpp:1620-1720): out_partial (n, b, s, h, d) fp32,
+    lse_partial (n, b, s, h) fp32 contiguous in the seqlen dimension; returns (out, softmax_lse (b, s, h) view of a
+    (b, h, s) buffer).  bf16 partials are accepted as well (what LiteAttention returns)."""
+    _check(out_partial.is_cuda and lse_partial.is_cuda, "out_partial / lse_partial must be CUDA tensors")
+    _check(out_partial.dtype in (torch.float32, torch.bfloat16),
+           "Attention combine function only support fp32 data type")                               # :1631 (+bf16)
+    _check(lse_partial.dtype == torch.float32, "Attention combine function only support fp32 data type")
+    _check(out_partial.dim() == 5 and lse_partial.dim() == 4, "out_partial must be 5-D, lse_partial 4-D")
+    _check(out_partial.stride(-1) == 1, "Input tensor must have contiguous last dimension")
+    _check(lse_partial.stride(-2) == 1, "LSE tensor must be contiguous in the seqlen dimension")
+    n, b, s, h, d = out_partial.shape
+    _check(n <= 8, "lite_attention::fwd_combine (sm_100a) supports at most 8 partial results")
+    _check(tuple(lse_partial.shape) == (n, b, s, h), "lse_partial must be (num_splits, batch, seqlen, heads)")
+    _check(d % 8 == 0, "head_dim must be a multiple of 8")
+    out_type = out_dtype if out_dtype is not None else out_partial.dtype
+    _check(out_type in (torch.float32, torch.bfloat16), "Output type must be FP32 or BF16")        # (fp16 not built)
+    if out is not None:
+        _check(out.dtype == out_type and out.device == out_partial.device and tuple(out.shape) == (b, s, h, d)
+               and out.is_contiguous(), "out must be a contiguous (batch, seqlen, heads, head_dim) tensor of out_dtype")
+    else:
+        out = torch.empty((b, s, h, d), dtype=out_type, device=out_partial.device)
+    o_parts = [out_partial[i].contiguous() for i in range(n)]
+    l_parts = [lse_partial[i].transpose(1, 2).contiguous() for i in range(n)]      # (b, h, s), a view when stride(-2)==1
+    lse = torch.empty((b, h, s), dtype=torch.float32, device=out_partial.device)
+    if b * s > 0:
+        _native.combine(o_parts, l_parts, out, lse)
+    return out, lse.transpose(1, 2)
 
 
 def _register():
     lib = torch.library.Library("lite_attention", "DEF")
     lib.define(_FWD_SCHEMA)
     lib.impl("fwd", _fwd_cuda, "CUDA")
+    lib.define(_COMBINE_SCHEMA)
+    lib.impl("fwd_combine", _fwd_combine_cuda, "CUDA")
     for name, schema in _STUB_SCHEMAS.items():
         lib.define(schema)
 
@@ -252,8 +387,15 @@ def flash_attn_combine(out_partial, lse_partial, out: Optional[torch.Tensor] = N
     for o, l in zip(o_parts, l_parts):
         _check(o.is_cuda and o.dtype == torch.bfloat16 and o.shape == (b, s, h, d), "flash_attn_combine: bad out part")
         _check(l.shape == (b, h, s), "flash_attn_combine: bad lse part")
+    dev = o_parts[0].device
+    _check(all(o.device == dev for o in o_parts) and all(l.device == dev for l in l_parts),
+           "flash_attn_combine: all parts must be on one device")
     if out is None:
         out = torch.empty_like(o_parts[0])
+    else:
+        _check(out.dtype in (torch.bfloat16, torch.float32) and tuple(out.shape) == (b, s, h, d)
+               and out.is_contiguous() and out.device == dev,
+               "flash_attn_combine: out must be a contiguous (batch, seqlen, heads, d) bf16/fp32 tensor on the parts' device")
     lse = torch.empty((b, h, s), dtype=torch.float32, device=out.device) if return_lse else None
     _native.combine(o_parts, l_parts, out, lse)
     return (out, lse) if return_lse else out

@@ -18,7 +18,7 @@ from typing import Optional, Tuple, Union
 import torch
 
 from . import _native
-from .flash_attn_interface import _flash_attn_forward, flash_attn_func
+from .flash_attn_interface import _flash_attn_forward, flash_attn_func, fwd_peer_scatter
 
 
 class LiteAttention:
@@ -228,16 +228,8 @@ class LiteAttention:
             # Sequence-parallel return path (liteattention_b200/dist.py): O rows are scattered to the peers that own
             # their tokens by the kernel's epilogue.  Not expressible through the reference's op (its `out` is one
             # tensor), so this goes to the C ABI directly with the same list handling.
-            b, sq, h, d = query.shape
-            sc = scale if scale is not None else d ** (-0.5)
-            lse = torch.empty((b, h, sq), dtype=torch.float32, device=query.device)
-            if read_list is not None and write_list is not None:
-                stat = torch.empty((b, h) + tuple(read_list.shape[-2:-1]) + (read_list.shape[-1] - 1,),
-                                   dtype=torch.float32, device=query.device)
-                _native.fwd_skip(query, key, value, out, lse, sc, read_list, must_do_list_expanded, write_list, stat,
-                                 self.threshold)
-            else:
-                _native.fwd(query, key, value, out, lse, sc, read_list, None)
+            lse = fwd_peer_scatter(query, key, value, out, scale, read_list, must_do_list_expanded, write_list,
+                                   self.threshold)
             output = (out, lse) if return_softmax_lse else out
         elif out is None:
             output = flash_attn_func(q=query, k=key, v=value, softmax_scale=scale, attn_read_list=read_list,

@@ -8,7 +8,8 @@ Tolerances (stated here, as the north star asks):
   LSE : 1e-3 absolute (the reference's own check is 0.1, test_lite_attention.py:89).
   skip statistic : 2e-4 absolute against the oracle's fp32 statistic (different summation orders);
   skip list      : BIT-EXACT against the C codec oracle fed with the kernel's own statistic; against the
-                   oracle's own statistic every disagreeing tile must be a threshold tie (|stat - thr| < 1e-3).
+                   oracle's own statistic every disagreeing tile must be a threshold tie as SURVEY.md 8(c) defines
+                   it: |stat - thr| < 1e-4 * max(1, |thr|).
 """
 import math
 
@@ -23,6 +24,12 @@ from tests import helpers as H
 pytestmark = pytest.mark.gpu
 
 DEV = "cuda"
+
+
+def _tie(stat, thr):
+    """S differs in the last ulps between tcgen05 and CPU summation orders, so a vote may
+    differ only where the statistic sits on the threshold."""
+    return (stat - thr).abs() < 1e-4 * max(1.0, abs(thr))
 
 
 def _qkv(b, sq, h, d=128, sk=None, hk=None, seed=0, scale=1.0):
@@ -120,8 +127,7 @@ def test_list_gated_matches_oracle(native_lib, b, s, h, p_keep, thr):
         vote_k = ~(st > thr) & vis
         vote_o = ~(ora["stat"] > thr) & vis
         diff = vote_k != vote_o
-        assert diff.any() and ((ora["stat"][diff] - thr).abs() < 1e-3).all()
-        assert diff.float().mean() < 1e-3
+        assert diff.any() and _tie(ora["stat"][diff], thr).all()
 
 
 def test_must_do_list_matches_oracle(native_lib):
@@ -156,29 +162,71 @@ def _local_qk(b, s, h, seed=3, amp=16.0):
 
 
 def test_multi_timestep_trajectory_matches_oracle(native_lib):
-    """Chained calls on one LiteAttention object (evolving QK-Skip, config C3 in miniature): the list after every
-    step equals the oracle's chained list; sparsity is monotone and becomes non-trivial."""
+    """Chained calls on one LiteAttention object (evolving QK-Skip, config C3 in miniature), 12 steps: after EVERY
+    step every list row equals the oracle's own chained row bit for bit, except rows that contain a tile sitting on
+    the threshold (SURVEY 8(c) tie); only those rows are re-seeded from the kernel so the two chains stay comparable.
+    Sparsity is monotone and becomes non-trivial."""
     from liteattention_b200 import LiteAttention
     b, s, h, thr = 1, 2600, 2, -10.0
     qt, kt = H.tiles(s)
     la = LiteAttention(enable_skipping=True, threshold=thr, max_batch_size=b)
     rl_o = H.init_list(b, h, qt, kt)
     prev_sp = -1.0
-    for step in range(4):
+    tied_rows_total = 0
+    for step in range(12):
         q, k, v = _local_qk(b, s, h, seed=3 + step)
         ora = oa.lite_attention_oracle(q, k, v, None, rl_o, None, thr=thr)
         out = la(q.to(DEV), k.to(DEV), v.to(DEV))
         _assert_close(out.cpu(), ora["lse"], ora["out_f32"], ora["lse"])
         got = la.read_list[:b].cpu()
         vis = ~torch.isnan(ora["stat"])
-        near_tie = ((ora["stat"] - thr).abs() < 1e-3) & vis
-        if not near_tie.any():
-            assert H.rows_equal_upto_len(got.view(-1, kt + 1).numpy(), ora["write_list"].view(-1, kt + 1).numpy()), step
+        tied_row = (_tie(ora["stat"], thr) & vis).any(dim=-1).view(-1)             # [b*h*qt]
+        g2, o2 = got.view(-1, kt + 1).numpy(), ora["write_list"].view(-1, kt + 1).numpy()
+        clean = (~tied_row).numpy()
+        assert H.rows_equal_upto_len(g2[clean], o2[clean]), f"step {step}: a non-tied row differs from the oracle"
+        tied_rows_total += int(tied_row.sum())
         sp = la.last_sparsity(b)
         assert sp >= prev_sp - 1e-9
         prev_sp = sp
-        rl_o = got.clone()          # keep both chains on the same list even if a tie ever flipped a vote
+        rl_o = ora["write_list"].clone()
+        rl_o.view(-1, kt + 1)[tied_row] = got.view(-1, kt + 1)[tied_row]          # tied rows only
     assert prev_sp > 0.15, f"expected real sparsity on local attention maps, got {prev_sp}"
+    assert tied_rows_total <= 0.02 * 12 * b * h * qt, "ties must be rare"
+
+
+def test_wan_shape_spot_check(native_lib):
+    """The benchmarked configuration itself: S = 75 600 (591 Q tiles, the last with 80 rows; 430 K tiles, the last with
+    96 columns), 42 % lists -- the balanced synthetic one bench.py uses AND a Bernoulli one (unequal rows).  Q tiles
+    0, 297 and 590: O / LSE against the fp32 masked reference, visited tile set and statistic against the oracle."""
+    from liteattention_b200 import synth
+    b, s, h = 1, 75600, 2
+    g = torch.Generator(device=DEV).manual_seed(0)
+    q, k, v = (torch.randn(b, s, h, 128, device=DEV, generator=g).to(torch.bfloat16) for _ in range(3))
+    qt, kt = H.tiles(s)
+    assert (qt, kt) == (591, 430)
+    spots = (0, 297, 590)
+    lists = {"balanced": synth.exact_sparsity_list(b, h, qt, kt, 0.42, seed=1234, device=DEV),
+             "bernoulli": synth.random_skip_list(b, h, qt, kt, 0.42, seed=99, device=DEV)}
+    qc, kc, vc = q.cpu(), k.cpu(), v.cpu()
+    for name, (rl, keep) in lists.items():
+        assert keep[..., kt - 1].all()
+        out = torch.empty_like(q)
+        lse = torch.empty(b, h, s, device=DEV)
+        stat = torch.full((b, h, qt, kt), float("nan"), device=DEV)
+        native_lib.fwd(q, k, v, out, lse, 128 ** -0.5, rl, stat)
+        torch.cuda.synchronize()
+        ora = oa.lite_attention_oracle(qc, kc, vc, None, rl.cpu(), None, thr=-10.0, q_tiles=spots)
+        for m in spots:
+            rows = slice(m * 128, min((m + 1) * 128, s))
+            o_ref, lse_ref = _masked_ref(q[:, rows], k, v, keep[:, :, m:m + 1])
+            _assert_close(out[:, rows], lse[:, :, rows], o_ref, lse_ref)
+            _assert_close(out[:, rows].cpu(), lse[:, :, rows].cpu(), ora["out_f32"][:, rows], ora["lse"][:, :, rows])
+            st, so = stat[:, :, m].cpu(), ora["stat"][:, :, m]
+            assert torch.equal(torch.isnan(st), torch.isnan(so)), f"{name}: visited tile set differs at Q tile {m}"
+            assert torch.equal(~torch.isnan(st), keep[:, :, m].cpu()), f"{name}: visited tiles are not the listed ones"
+            fin = torch.isfinite(so)
+            assert (st[fin] - so[fin]).abs().max() < 2e-4
+            assert torch.equal(torch.isinf(st), torch.isinf(so))
 
 
 def test_reference_smoke_invariants_through_the_api(native_lib):

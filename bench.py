@@ -45,7 +45,11 @@ def parse_args():
                          "nccl = NCCL gather pipelined by head group")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--sweep", action="store_true", help="also time sparsity 0/21/42/57/77 % (kernel only)")
+    ap.add_argument("--no-comparators", action="store_true", help="skip the dense GPU comparators (N=1 only)")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the live ncu DRAM-traffic measurement (N=1 only)")
+    ap.add_argument("--no-seqpar", action="store_true", help="N>1: skip the sequence-parallel (one prompt over N GPUs) leg")
+    ap.add_argument("--sweep", action="store_true", help="time sparsity 0/21/42/57/77 % instead of 0/42/77 % (kernel only)")
+    ap.add_argument("--must-do", action="store_true", help="also time the update kernel with a must-do list (text tokens)")
     return ap.parse_args()
 
 
@@ -76,12 +80,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 10))
-    r = cpu_sdpa_sample(args.seq, steps, max(1, min(args.warmup, 2)))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)      # a step = the bounded slice below (~70 ms on 16+ cores)
+    r = cpu_sdpa_sample(args.seq, steps, warmup)
     dense = 4.0 * args.heads * args.seq * float(args.seq) * D_WAN
     line = {
         "impl": "reference", "metric": METRIC, "value": r["tflops"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": max(1, min(args.warmup, 2)),
+        "steps": steps, "warmup": warmup,
         "ms_per_step": dense / (r["tflops"] * 1e12) * 1e3,      # extrapolated to one full B=1 call
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"Wan2.1-14B self-attention shape B=1 S={args.seq} H={args.heads} D=128, dense on CPU "
@@ -144,6 +148,57 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Best effort: run this process (and so first-touch its pinned buffers) on the CPUs of the GPU's NUMA node."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(gpu_index)],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        bus = bus[-12:] if len(bus) > 12 else bus              # 00000000:1B:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return "unknown (numa_node = -1)"
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & set(cpus)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return f"{node} (bound to {len(allowed)} cpus)"
+        return f"{node} (not bound: no allowed cpu on that node)"
+    except Exception as e:  # noqa: BLE001
+        return f"unknown ({type(e).__name__})"
+
+
+def measure_dram_traffic(args):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE la_fwd_kernel launch at this run's configuration, measured by
+    running tools/one_launch.py under ncu in a subprocess (after the timed regions; never timed).  Returns (bytes, source)
+    or (None, reason)."""
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    script = os.path.join(ROOT, "tools", "one_launch.py")
+    if not os.path.exists(ncu) or not os.path.exists(script):
+        return None, "ncu or tools/one_launch.py not found"
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k",
+           "regex:la_fwd_kernel", "-s", "2", "-c", "1", "--csv", sys.executable, script, "--seq", str(args.seq),
+           "--heads", str(args.heads), "--sparsity", str(args.sparsity)]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=300).stdout
+        tot = 0.0
+        found = 0
+        for ln in out.splitlines():
+            if "dram__bytes_" in ln:
+                cols = [c.strip().strip('"') for c in ln.split('","')]
+                unit, val = cols[-2].lower(), float(cols[-1].replace(",", ""))
+                tot += val * {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1.0)
+                found += 1
+        if found >= 2:
+            return tot, "ncu subprocess in this run (one launch, dram__bytes_read.sum + dram__bytes_write.sum)"
+        return None, "ncu produced no dram__bytes rows: " + out[-160:].replace("\n", " | ")
+    except Exception as e:  # noqa: BLE001
+        return None, f"{type(e).__name__}: {str(e)[:120]}"
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     args = parse_args()
@@ -182,8 +237,8 @@ def main():
         return rl
 
     # ---- kernel-level timing: forward + update as two C-ABI calls with CUDA events around each ------------
-    def time_kernels(sp, steps, warmup):
-        rl = make_list(sp, H, seed=1234)
+    def time_kernels(sp, steps, warmup, rl=None, must_do=None):
+        rl = make_list(sp, H, seed=1234) if rl is None else rl
         wl = torch.zeros_like(rl)
         out = torch.empty_like(q)
         lse = torch.empty(B, H, S, device=dev, dtype=torch.float32)
@@ -192,13 +247,13 @@ def main():
         ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
         for _ in range(warmup):
             _native.fwd(q, k, v, out, lse, scale, rl, stat)
-            _native.skip_update(rl, None, wl, stat, B, H, qt, kt, float("-inf"))
+            _native.skip_update(rl, must_do, wl, stat, B, H, qt, kt, float("-inf"))
         torch.cuda.synchronize()
         for i in range(steps):
             ev[i][0].record()
             _native.fwd(q, k, v, out, lse, scale, rl, stat)
             ev[i][1].record()
-            _native.skip_update(rl, None, wl, stat, B, H, qt, kt, float("-inf"))
+            _native.skip_update(rl, must_do, wl, stat, B, H, qt, kt, float("-inf"))
             ev[i][2].record()
         torch.cuda.synchronize()
         assert torch.equal(wl[..., 0], rl[..., 0])              # thr = -inf: the list is stationary
@@ -247,9 +302,75 @@ def main():
         ms, launches = float(mx[0]), int(sm[1])
     step_sparsity = statistics.mean(a.last_sparsity(B) for a in bp.attn)
 
+    # ---- N>1: did rank 0 receive what every rank computed?  (driver-visible correctness of the gather) ----
+    gather_verified = None
+    if world > 1:
+        def checksum(t):                                        # order-sensitive 2 x int64 digest of a bf16 tensor
+            x = t.contiguous().view(torch.int16).to(torch.int64).view(-1)
+            w = (torch.arange(x.numel(), device=x.device, dtype=torch.int64) % 8191) + 1
+            return torch.stack([x.sum(), (x * w).sum()])
+        _, gathered = bp(q, k, v)                               # thr = -inf: lists are stationary, O repeats bit for bit
+        torch.cuda.synchronize()
+        local = torch.empty_like(q)                             # the same call into a LOCAL buffer, one head group at a time
+        for gi, gsl in enumerate(bp.groups):
+            chk = factory()
+            chk.load_skip_list(bp.attn[gi].read_list[:B].clone(), q[:, :, gsl], v[:, :, gsl])
+            local[:, :, gsl] = chk(q[:, :, gsl], k[:, :, gsl], v[:, :, gsl])
+        mine = checksum(local)
+        allsums = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allsums, mine)
+        if rank == 0:
+            ok = True
+            for r in range(world):
+                slab = torch.cat([gathered[gi][r] for gi in range(len(gathered))], dim=2) if len(gathered) > 1 else gathered[0][r]
+                ok &= bool(torch.equal(checksum(slab), allsums[r]))
+            gather_verified = ok
+        del local
+        barrier()
+
+    # ---- N>1: one prompt over N GPUs (sequence-parallel): all_to_all in, O scattered by the epilogue ----
+    seqpar = None
+    if world > 1 and not args.no_seqpar and S % world == 0 and H % world == 0:
+        try:
+            from liteattention_b200.dist import UlyssesLiteAttention
+            sl_ = S // world
+            gsp = torch.Generator(device=dev).manual_seed(4242)              # same seed on every rank: one shared prompt
+            qf, kf, vf = (torch.randn(B, S, H, D, device=dev, generator=gsp).to(torch.bfloat16) for _ in range(3))
+            loc = slice(rank * sl_, (rank + 1) * sl_)
+            ql, kl, vl = (t[:, loc].contiguous() for t in (qf, kf, vf))
+            ul = UlyssesLiteAttention(lambda: LiteAttention(enable_skipping=False, max_batch_size=B))
+            for _ in range(2):
+                o_sp = ul(ql, kl, vl)
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            nsp = max(3, min(args.steps, 10))
+            for _ in range(nsp):
+                o_sp = ul(ql, kl, vl)
+            s1.record()
+            barrier()
+            sp_ms = torch.tensor([s0.elapsed_time(s1) / nsp], device=dev, dtype=torch.float64)
+            dist.all_reduce(sp_ms, op=dist.ReduceOp.MAX)
+            # correctness: my tokens, the heads of rank (rank+1)%world, against a single-GPU dense call on those heads
+            hl = H // world
+            hsl = slice(((rank + 1) % world) * hl, ((rank + 1) % world + 1) * hl)
+            ref_o = LiteAttention(enable_skipping=False, max_batch_size=B)(qf[:, :, hsl], kf[:, :, hsl], vf[:, :, hsl])
+            okt = torch.tensor([int(torch.equal(o_sp[:, :, hsl], ref_o[:, loc]))], device=dev)   # same Q tiling => bit-exact
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            seqpar = {"ms_per_call": float(sp_ms[0]), "verified_bit_exact_vs_single_gpu": bool(int(okt[0])),
+                      "config": f"one dense Wan-shape prompt (S={S}, H={H}) sequence-sharded over {world} GPUs: all_to_all of "
+                                "q/k/v (NCCL), forward on H/N heads, O rows stored by the epilogue into the owning rank's "
+                                "symmetric buffer (peer stores over NVLink)",
+                      "effective_tflops": dense_flops / (float(sp_ms[0]) * 1e-3) / 1e12}
+            del qf, kf, vf, ql, kl, vl, ul, o_sp
+        except Exception as e:  # noqa: BLE001 -- auxiliary leg; the headline does not depend on it
+            seqpar = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+        barrier()
+
     # ---- end to end through LiteAttention.__call__ with pinned host buffers ---------------------------------
     e2e = None
     if not args.no_e2e:
+        numa_note = bind_to_gpu_numa_node(local_rank)            # pinned buffers land on the GPU's own NUMA node
         hq, hk, hv = (t.cpu().pin_memory() for t in (q, k, v))
         ho = torch.empty(B, S, H, D, dtype=torch.bfloat16).pin_memory()
         dbuf = [[torch.empty_like(q) for _ in range(3)] for _ in range(2)]
@@ -293,9 +414,32 @@ def main():
             t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_ms = float(t[0])
+        # what the copies alone achieve on this host with all ranks copying at once (the e2e ceiling when N ranks share it)
+        barrier()
+        e0.record()
+        for _ in range(3):
+            for dst_, src_ in zip(dbuf[0], (hq, hk, hv)):
+                dst_.copy_(src_, non_blocking=True)
+        e1.record()
+        barrier()
+        h2d_gbs = 3 * 3 * q.numel() * 2 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        e0.record()
+        for _ in range(3):
+            ho.copy_(dbuf[0][0], non_blocking=True)
+        e1.record()
+        barrier()
+        d2h_gbs = 3 * q.numel() * 2 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        bw = torch.tensor([h2d_gbs, d2h_gbs], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(bw, op=dist.ReduceOp.SUM)
+        copy_floor_ms = max(3 * q.numel() * 2 * world / (float(bw[0]) * 1e9), q.numel() * 2 * world / (float(bw[1]) * 1e9)) * 1e3
         e2e = {"value": dense_flops * world / (e2e_ms * 1e-3) / 1e12, "unit": UNIT, "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": 3 * q.numel() * 2 * world, "d2h_bytes_per_step": q.numel() * 2 * world,
-               "api": "LiteAttention.__call__ on pinned host q/k/v -> host O, double-buffered copies"}
+               "api": "LiteAttention.__call__ on pinned host q/k/v -> host O, double-buffered copies",
+               "host_link": {"aggregate_h2d_gbs": float(bw[0]), "aggregate_d2h_gbs": float(bw[1]),
+                             "copy_only_floor_ms_per_step": copy_floor_ms, "numa_node": numa_note,
+                             "limiter": ("host<->device copies (PCIe / host memory), all ranks through one host"
+                                         if copy_floor_ms > 0.8 * ms else "kernel")}}
         del hq, hk, hv, ho, dbuf, keep
 
     # ---- roofline of the dominant kernel (rank 0), sweep, CPU baseline -------------------------------------
@@ -309,12 +453,19 @@ def main():
         peak_burst = peaks.get("bf16_tflops", 1590.0)
         kt_main = time_kernels(args.sparsity, args.steps, args.warmup)
         achieved = kt_main["exec_flops"] / (kt_main["fwd_ms"] * 1e-3) / 1e12
-        traffic = None
-        tr_path = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tr_path):
-            traffic = json.load(open(tr_path)).get("la_fwd_kernel", {}).get("dram_bytes_per_launch")
+        traffic, traffic_src = None, None
+        if world == 1 and not args.no_traffic:
+            traffic, traffic_src = measure_dram_traffic(args)       # one launch under ncu, after the timed regions
+        if traffic is None:
+            tr_path = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(tr_path):
+                tj = json.load(open(tr_path)).get("la_fwd_kernel", {})
+                traffic = tj.get("dram_bytes_per_launch")
+                traffic_src = "profiles/traffic.json (" + str(tj.get("source", "earlier ncu capture")) + ")" + \
+                              ("" if traffic_src is None else "; live measurement failed: " + traffic_src)
         roofline = {"bound": "tensor", "kernel": "la_fwd_kernel", "achieved": achieved, "peak": peak_sust,
-                    "unit": "TFLOP/s", "frac": achieved / peak_sust, "traffic": traffic,
+                    "unit": "TFLOP/s", "frac": achieved / peak_sust, "traffic": traffic, "traffic_source": traffic_src,
+                    "algorithmic_bytes_per_launch": 4.0 * q.numel() * 2 + B * H * S * 4 + 2.0 * B * H * qt * (kt + 1) * 4,
                     "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
                                     if peaks else "fallback"),
                     "frac_of_burst_peak": achieved / peak_burst, "kernel_ms": kt_main["fwd_ms"],
@@ -356,14 +507,51 @@ def main():
             del xq
         except Exception as e:  # noqa: BLE001  (auxiliary line only; the headline numbers do not depend on it)
             aux = {"rope_cast_fp32_to_bf16": {"error": str(e)[:200]}}
-        sweep = None
-        if args.sweep:
-            sweep = []
-            for sp in (0.0, 0.21, 0.42, 0.57, 0.77):
-                r = time_kernels(sp, max(5, args.steps // 2), 3)
-                sweep.append({"sparsity": round(r["sparsity"], 4), "fwd_ms": r["fwd_ms"], "update_ms": r["update_ms"],
-                              "effective_tflops": dense_flops / (r["fwd_ms"] + r["update_ms"]) / 1e9,
-                              "executed_tflops": r["exec_flops"] / r["fwd_ms"] / 1e9})
+        # the metric's other points (BASELINE.json: 0 / 42 / 77 %), kernel-level, same q/k/v -- and an UNBALANCED 42 % mask
+        # (Bernoulli per tile: rows differ in length) next to the balanced one the headline uses
+        sweep = []
+        for sp in ((0.0, 0.21, 0.42, 0.57, 0.77) if args.sweep else (0.0, 0.77)):
+            r = time_kernels(sp, max(5, args.steps // 2), 3)
+            sweep.append({"sparsity": round(r["sparsity"], 4), "mask": "balanced (every row skips the same number of tiles)",
+                          "fwd_ms": r["fwd_ms"], "update_ms": r["update_ms"],
+                          "effective_tflops": dense_flops / (r["fwd_ms"] + r["update_ms"]) / 1e9,
+                          "executed_tflops": r["exec_flops"] / r["fwd_ms"] / 1e9})
+        rl_b, _ = synth.random_skip_list(B, H, qt, kt, args.sparsity, seed=99, device=dev)
+        r = time_kernels(args.sparsity, max(5, args.steps // 2), 3, rl=rl_b)
+        sweep.append({"sparsity": round(r["sparsity"], 4), "mask": "bernoulli per tile (rows of unequal length)",
+                      "fwd_ms": r["fwd_ms"], "update_ms": r["update_ms"],
+                      "effective_tflops": dense_flops / (r["fwd_ms"] + r["update_ms"]) / 1e9,
+                      "executed_tflops": r["exec_flops"] / r["fwd_ms"] / 1e9})
+        sweep.sort(key=lambda e: e["sparsity"])
+        # update kernel with a must-do list (the README's text-token use case: the first 512 tokens are never skipped)
+        md = LiteAttention._expand_must_do_list([511, 0], (B, H, qt, kt + 1), q, v)
+        r = time_kernels(args.sparsity, max(5, args.steps // 2), 3, must_do=md)
+        roofline["update_kernel"]["ms_with_must_do_list"] = r["update_ms"]
+        del md
+        # dense GPU comparators on the same box, same q/k/v (context, not the reference)
+        comparators = None
+        if world == 1 and not args.no_comparators:
+            try:
+                from baseline.comparators import time_dense_comparators
+                comparators = time_dense_comparators(q, k, v, steps=max(3, min(args.steps, 5)), warmup=2)
+                ok = {n: c for n, c in comparators.items() if "ms" in c}
+                if ok:
+                    best = min(ok, key=lambda n: ok[n]["ms"])
+                    dense_ms = next(e["fwd_ms"] for e in sweep if e["sparsity"] == 0.0)
+                    pts = sorted((e["sparsity"], e["fwd_ms"]) for e in sweep if e["mask"].startswith("balanced")) + \
+                          [(kt_main["sparsity"], kt_main["fwd_ms"])]
+                    pts.sort()
+                    cross = None                      # sparsity at which la_fwd_kernel equals the best dense kernel (linear interp.)
+                    for (s0, m0), (s1, m1) in zip(pts, pts[1:]):
+                        if m0 >= ok[best]["ms"] >= m1 and m0 != m1:
+                            cross = s0 + (s1 - s0) * (m0 - ok[best]["ms"]) / (m0 - m1)
+                    comparators["summary"] = {"best_dense": best, "best_dense_ms": ok[best]["ms"], "la_fwd_dense_ms": dense_ms,
+                                              "la_fwd_dense_over_best": dense_ms / ok[best]["ms"],
+                                              "la_fwd_headline_ms": kt_main["fwd_ms"],
+                                              "speedup_of_headline_over_best_dense": ok[best]["ms"] / kt_main["fwd_ms"],
+                                              "crossover_sparsity": cross}
+            except Exception as e:  # noqa: BLE001
+                comparators = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
         cpu = None
         if not args.no_cpu and world == 1:
             c = cpu_sdpa_sample(S, 8, 1)
@@ -375,8 +563,9 @@ def main():
             "config": {"workload": f"Wan2.1-14B self-attention shape, B={B} per GPU, S={S}, H={H}, D={D}, bf16; "
                                    f"fixed random tile Skip-Mask at {step_sparsity:.1%} sparsity (128x176 tiles, runs of "
                                    "4), thr=-inf so the list is stationary; step = skip-list-gated forward + skip-list "
-                                   "update" + ("" if world == 1 else f"; batch-parallel, O gathered to rank 0 over NCCL "
-                                                                      f"in {n_groups} head groups"),
+                                   "update" + ("" if world == 1 else "; batch-parallel, one prompt per GPU, O gathered to rank 0 ("
+                                               + ("stored by the forward epilogue into rank 0's symmetric buffer over NVLink"
+                                                  if bp.peer_store else f"NCCL gather pipelined in {n_groups} head groups") + ")"),
                        "batch_per_gpu": B, "seq_len": S, "heads": H, "head_dim": D, "sparsity": step_sparsity,
                        "parallelism": f"batch-parallel x{world}" + ("" if world == 1 else (", O stored by the forward epilogue into rank 0's symmetric buffer over NVLink (fused gather)" if bp.peer_store else ", NCCL gather" + ("" if args.gather == "nccl" else " (peer-store setup failed: " + str(bp.fallback_reason) + ")"))),
                        "l2": "q/k/v/o = 3.1 GB per step >> 126 MB L2, no flush needed"},
@@ -384,8 +573,16 @@ def main():
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        if sweep is not None:
-            line["sweep"] = sweep
+        line["sweep"] = sweep
+        if comparators is not None:
+            line["gpu_comparators"] = comparators
+        if world > 1:
+            line["gather_verified"] = gather_verified
+            if seqpar is not None:
+                line["seq_parallel"] = seqpar
+            if e2e is not None:
+                e2e["note"] = ("per rank: every rank copies ITS prompt host->device and ITS O device->host (what a DiT "
+                               "pipeline does: each rank's O feeds its own next layer); not routed through the gather")
         line["derived_hopper_reference_ms"] = {"0%": 174, "42%": 104.5, "77%": 40.8,
                                                "note": "derived from README totals (BASELINE.md), H100-class, not measured"}
     if world > 1:

@@ -80,7 +80,8 @@ def lib():
         L.la_combine_sm100.argtypes = [ctypes.POINTER(CombineParams), _c_vp]
         L.la_rope_cast_sm100.argtypes = [ctypes.POINTER(RopeParams), _c_vp]
         L.la_watchdog_read.argtypes = [ctypes.POINTER(ctypes.c_uint * 4)]
-        if L.la_abi_version() != 3:
+        # LITEATTN_B200_LIB builds of older revisions (tools/ab.py) share the forward / update structs
+        if L.la_abi_version() != 3 and not os.environ.get("LITEATTN_B200_LIB"):
             raise RuntimeError("libliteattn_b200.so ABI version mismatch")
         _lib = L
     return _lib

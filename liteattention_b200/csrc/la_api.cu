@@ -204,6 +204,17 @@ int la_fwd_sm100(const la_fwd_params* p, void* stream_) {
     }
     a.rows_per_peer = p->out_rows_per_peer;
   }
+  {
+    // 256-bit stores need 32-byte aligned destinations: base pointers and row / head / batch strides
+    const int elt = p->out_is_f32 ? 4 : 2;
+    bool ok = ((p->o_batch_stride * elt) % 32 == 0) && ((p->o_row_stride * elt) % 32 == 0) && ((p->o_head_stride * elt) % 32 == 0);
+    if (a.rows_per_peer > 0) {
+      for (int i = 0; i < p->n_out_peers; ++i) ok = ok && (reinterpret_cast<uintptr_t>(p->out_peer[i]) % 32 == 0);
+    } else {
+      ok = ok && (reinterpret_cast<uintptr_t>(p->out) % 32 == 0);
+    }
+    a.o_align32 = ok ? 1 : 0;
+  }
   a.lse = p->lse;
   a.read_list = p->read_list;
   a.tile_stat = p->tile_stat;

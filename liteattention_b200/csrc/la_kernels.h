@@ -18,6 +18,7 @@ struct FwdKernelArgs {
   // r % rows_per_peer -- peer GPUs' buffers mapped over NVLink; `out` is ignored.
   __nv_bfloat16* out_peer[8];
   int32_t rows_per_peer;
+  int32_t o_align32;    // every O row segment the epilogue writes starts on a 32-byte boundary: 256-bit stores
   float* lse;
   const int32_t* read_list;
   float* tile_stat;

@@ -40,6 +40,19 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
   return done;
 }
 
+// Non-blocking poll (try_wait may suspend the thread for a system-dependent time before it answers "not yet").
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
+
 // Watchdog: a protocol bug must not hang the GPU box; after ~2^24 failed polls the waiting thread traps and the host
 // sees a launch failure instead of a timeout (compute-sanitizer then names the wait, the build has -lineinfo).
 // Deliberately nothing but a counter and a trap: a recording call here costs 3 % of the forward kernel (code bloat
@@ -113,6 +126,12 @@ __device__ __forceinline__ void tma_load_4d_hint(uint32_t smem_dst, const CUtens
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar),
         "l"(policy)
       : "memory");
+}
+// Warm L2 with a tile that a later tma_load_4d of the same coordinates will fetch.
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
 }
 // 4-D tiled store smem -> gmem (bulk async group).
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2,
@@ -251,6 +270,17 @@ __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+// 256-bit global store (sm_100: STG.E.256): one thread fills a whole 32-byte sector.  ptr must be 32-byte aligned.
+__device__ __forceinline__ void stg_v8(void* ptr, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ int lds_s32(uint32_t addr) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
 __device__ __forceinline__ void red_smax_s32(uint32_t addr, int v) {

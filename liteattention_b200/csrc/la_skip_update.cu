@@ -17,9 +17,12 @@
 //     like): the writer's state is reset at every range start, so ranges are independent: one LANE per range
 //     loads that range's statistics, packs the votes into a 64-bit mask, derives the transitions with two bit
 //     operations, and a warp prefix sum places each lane's entries.  ~5x fewer instructions than the tile walk.
-//   * tile-parallel (sorted, no must-do, some long range -- dense or early lists): lanes map to K tiles, the state
-//     machine collapses to neighbour compares + ballot prefix sums over smem bitmaps.
-//   * general (must-do list present, or a hand-made unsorted list): lane 0 walks the row serially.
+//   * tile-parallel (sorted; some long range -- dense or early lists -- or a must-do list): lanes map to K tiles, the
+//     state machine collapses to neighbour compares + ballot prefix sums over smem bitmaps.  The must-do reader is a
+//     "lagging follower": on every skip-voted tile it moves at most one range towards the range that contains the
+//     tile, m_k = min(m_{k-1} + 1, R_k)  =>  m_k = k + min_{j <= k}(R_j - j): a warp prefix-min over the skip-voted
+//     tiles in visit order (round 2; it used to send the whole row to one lane).
+//   * general (a hand-made unsorted list, or a must-do row with more than 32 or unsorted ranges): lane 0 walks the row.
 //
 // Bounds: the reference writer has no capacity check and can overflow a row into its neighbour
 // (SURVEY.md section 8 a12-iii).  Here a row that would need more than `ktiles` entries is replaced by a
@@ -81,10 +84,33 @@ __global__ void __launch_bounds__(kUpdWarpsPerBlock * 32) la_skip_update_kernel(
 
   // ---- classify: is the must-do row trivial, is the read row sorted/disjoint?
   bool general = false;
+  bool with_md = false;            // a non-trivial must-do row that the tile-parallel path can handle
+  int md_s = 0, md_e = 0, md_n = 0;   // lane j holds must-do range j (start, end); ranges >= md_n are the (0, 0) padding
   if (md != nullptr) {
     const int mdlen = md[0];
     // `[2, 0, 0]` (lite_attention.py:229-231 default) protects nothing: n <= 0 && n > 0 is never true.
-    if (!(mdlen <= 0 || (mdlen == 2 && md[1] == 0 && md[2] == 0))) general = true;
+    if (!(mdlen <= 0 || (mdlen == 2 && md[1] == 0 && md[2] == 0))) {
+      md_n = min(mdlen, ktiles) >> 1;
+      // What the serial reader sees past the listed ranges is whatever follows in the row: the expanded lists are
+      // zero-padded (lite_attention.py:236-238); the parallel path relies on that and on descending, disjoint ranges.
+      bool ok = (mdlen > 0) && (mdlen % 2 == 0) && md_n <= 32 && (2 * md_n + 2 <= ktiles);
+      if (ok) {
+        if (lane < md_n) {
+          md_s = md[1 + 2 * lane];
+          md_e = md[2 + 2 * lane];
+        }
+        const int nxt_s = __shfl_down_sync(0xffffffffu, md_s, 1);
+        bool bad = false;
+        if (lane < md_n) {
+          if (md_s < md_e || md_e < 0) bad = true;
+          if (lane + 1 < md_n && !(md_e > nxt_s)) bad = true;        // strictly descending, disjoint
+        }
+        if (lane == 0 && (md[1 + 2 * md_n] != 0 || md[2 + 2 * md_n] != 0)) bad = true;   // padding must be (0, 0)
+        ok = !__any_sync(0xffffffffu, bad);
+      }
+      if (ok) with_md = true;
+      else general = true;
+    }
   }
   int first_n = min(rd[1], ktiles - 1);
   int w = 1;  // next write slot
@@ -109,7 +135,7 @@ __global__ void __launch_bounds__(kUpdWarpsPerBlock * 32) la_skip_update_kernel(
   }
   if (!sorted_ok) general = true;
 
-  if (!general && short_ok) {
+  if (!general && short_ok && !with_md) {
     // ---------------------------------------------------------------- range-parallel path
     for (int r0 = 0; r0 < nranges; r0 += 32) {
       const int r = r0 + lane;
@@ -197,6 +223,8 @@ __global__ void __launch_bounds__(kUpdWarpsPerBlock * 32) la_skip_update_kernel(
   if (!general) {
     // ---------------------------------------------------------------- tile-parallel path
     bool carry_ev = true;  // effective vote of the previous (higher) tile; irrelevant at range starts
+    int md_k = 0;          // skip-voted tiles seen so far (visit order = descending tile index)
+    int md_min = 0;        // min(m_0, min_j (R_j - j)) over them, m_0 = 0: the follower's position is k + md_min
     // Four 32-tile chunks per trip: their statistic loads are issued together (the walk itself is a serial
     // ballot/prefix chain, so without this every chunk would expose one full HBM latency).
     constexpr int kUnroll = 4;
@@ -224,7 +252,27 @@ __global__ void __launch_bounds__(kUpdWarpsPerBlock * 32) la_skip_update_kernel(
         const bool v = vv[u], st = stt[u], en = enn[u];
         bool rv = false;  // raw vote: true = skip
         if (v && n != first_n) rv = !(sv[u] > thr);
-        const bool ev = rv;
+        bool ev = rv;
+        if (with_md) {
+          // R = first must-do range whose end is <= n (ranges are descending; index md_n = the (0, 0) padding).
+          // The serial reader tests `end > n` on every skip-voted tile and then moves ONE range (writer :156-159).
+          int R = 0;
+          for (int j = 0; j < md_n; ++j) R += (__shfl_sync(0xffffffffu, md_e, j) > n) ? 1 : 0;
+          const uint32_t mv = __ballot_sync(0xffffffffu, rv);
+          const int k = md_k + __popc(mv & ((1u << lane) - 1u)) + 1;     // 1-based rank of this tile among skip votes
+          int cand = rv ? (R - k) : 0x3fffffff;                           // R_k - k, only skip-voted tiles take part
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {                              // inclusive prefix min in lane (= visit) order
+            const int o = __shfl_up_sync(0xffffffffu, cand, d);
+            if (lane >= d) cand = min(cand, o);
+          }
+          const int run_min = min(md_min, cand);
+          const int m = rv ? min(k + run_min, md_n) : 0;                  // range the reader points at AFTER its single step
+          const int ms = __shfl_sync(0xffffffffu, md_s, m & 31), me = __shfl_sync(0xffffffffu, md_e, m & 31);
+          if (rv && m < md_n && n <= ms && n > me) ev = false;            // protected: the vote becomes "do"
+          md_min = min(md_min, __shfl_sync(0xffffffffu, cand, 31));
+          md_k += __popc(mv);
+        }
         bool prev_ev = __shfl_up_sync(0xffffffffu, ev, 1);
         if (lane == 0) prev_ev = carry_ev;
         const bool ps = st ? true : prev_ev;

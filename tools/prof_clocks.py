@@ -20,9 +20,9 @@ L.la_prof_read(buf, 1)
 v_ = list(buf)
 tiles = v_[6]
 ms = e0.elapsed_time(e1)
-print(f"kernel {ms:.3f} ms ({4*B*H*S*S*D/ms/1e9:.0f} TFLOP/s), tiles {tiles}, per-SM tiles {tiles/148:.0f}, "
+print(f"kernel {ms:.3f} ms ({4*B*H*S*S*D/ms/1e9:.0f} TFLOP/s), speculative tiles {tiles}, per-SM tiles {tiles/148:.0f}, "
       f"=> {ms*1e-3/(tiles/148)*1e9:.0f} ns per tile per SM")
-names = ["wait::ld S(i)", "exp loop (max posted mid-way) + try_wait", "xchg sync + verdict", "P st + prefetch issue", "publish", "exact tile (total)"]
+names = ["wait::ld S(i)", "exp loop + xchg + try_wait", "verdict", "P st + prefetch issue", "publish", "exact tile (total)"]
 for base, tag in ((0, "warp 0 (cols 0-87)"), (20, "warp 4 (cols 88-175)")):
     tot = 0
     print(f" softmax {tag}")
@@ -38,12 +38,11 @@ for j, nm in enumerate(names):
     per = v_[8 + j] / max(tiles, 1); tot += per
     print(f"   {nm:28s} {per:8.0f} clk/tile")
 print(f"   {'total':28s} {tot:8.0f} clk/tile")
-print(" producer")
+print(" TMA lane")
 for j, nm in enumerate(["wait K empty", "wait V empty"]):
     print(f"   {nm:28s} {v_[16 + j] / max(tiles, 1):8.0f} clk/tile")
-
 if v_[31]:
     n = v_[31]
-    print(f" per CTA ({n} CTAs, {tiles / n:.1f} tiles each): entry -> S(0) ready {v_[27] / n:.0f} clk, first (exact) tile {v_[28] / n:.0f}, "
-          f"epilogue {v_[29] / n:.0f}, whole CTA {v_[30] / n:.0f} clk  => fixed part ~{(v_[27] + v_[28] + v_[29]) / n:.0f} clk "
-          f"= {(v_[27] + v_[28] + v_[29]) / max(v_[30], 1) * 100:.1f} % of the CTA")
+    print(f" per item ({n} items, {tiles / n:.1f} speculative tiles each): descriptor -> S(0) ready {v_[27] / n:.0f} clk, first (exact) tile {v_[28] / n:.0f}, "
+          f"epilogue {v_[29] / n:.0f}, whole item {v_[30] / n:.0f} clk  => fixed part ~{(v_[27] + v_[28] + v_[29]) / n:.0f} clk "
+          f"= {(v_[27] + v_[28] + v_[29]) / max(v_[30], 1) * 100:.1f} % of the item")

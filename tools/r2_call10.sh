@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_fwd_gpu.py -m gpu -x -q > gpurun_out/c10_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/c10_pytest.log
+tail -4 gpurun_out/c10_pytest.log
+timeout 900 python tools/ab.py --rounds 1 --secs 1.0 r1=tools/_build/lib_r1.so pers200=- pers208=tools/_build/lib_r208.so pers216=tools/_build/lib_r216.so > gpurun_out/c10_ab.txt 2>&1
+cat gpurun_out/c10_ab.txt
+S=75600 H=40 LITEATTN_B200_LIB=$PWD/tools/_build/lib_prof.so timeout 300 python tools/prof_clocks.py > gpurun_out/c10_prof.txt 2>&1
+cat gpurun_out/c10_prof.txt

@@ -45,14 +45,25 @@ __device__ __forceinline__ void st_cols(uint32_t a, const uint32_t* r) {   // CO
   else { tmem_st_x16(a, r); tmem_st_x4(a + 16, r + 16); tmem_st_x2(a + 20, r + 20); }
 }
 
-// One tile's worth of work for one thread: COLS columns of one row.
-template <int COLS, uint32_t MASK, int ROWSUM, int ORDERED>
-__device__ __forceinline__ void body(const float* s, uint32_t* pr, uint64_t c2, uint64_t nm2, float& m_half, float& sum) {
+// One tile's worth of work for one thread: COLS columns of one row.  SPLIT: the row max of ALL columns is taken during
+// the first half of the loop and handed to `post` at the midpoint, so that an exchange can run under the second half.
+template <int COLS, uint32_t MASK, int ROWSUM, int ORDERED, int SPLIT, typename Post>
+__device__ __forceinline__ void body(const float* s, uint32_t* pr, uint64_t c2, uint64_t nm2, float& m_half, float& sum, Post post) {
   uint64_t acc0 = pack2(0.f, 0.f), acc1 = pack2(0.f, 0.f);
   float mx0 = -INFINITY, mx1 = -INFINITY;
+  constexpr int Q = COLS / 4, QH = (Q + 1) / 2;
 #pragma unroll
-  for (int j = 0; j < COLS; j += 4) {
-    mx0 = fmax3(mx0, s[j], s[j + 1]); mx1 = fmax3(mx1, s[j + 2], s[j + 3]);
+  for (int q = 0; q < Q; ++q) {
+    const int j = 4 * q;
+    if (SPLIT) {
+      if (q < QH) {
+        mx0 = fmax3(mx0, s[j], s[j + 1]); mx1 = fmax3(mx1, s[j + 2], s[j + 3]);
+        if (q + QH < Q) { mx0 = fmax3(mx0, s[j + 4 * QH], s[j + 4 * QH + 1]); mx1 = fmax3(mx1, s[j + 4 * QH + 2], s[j + 4 * QH + 3]); }
+      }
+      if (q == QH) { m_half = fmaxf(mx0, mx1); post(m_half); }
+    } else {
+      mx0 = fmax3(mx0, s[j], s[j + 1]); mx1 = fmax3(mx1, s[j + 2], s[j + 3]);
+    }
     float t0, t1, t2, t3, p0, p1, p2, p3;
     unpack2(ffma2(pack2(s[j], s[j + 1]), c2, nm2), t0, t1);
     unpack2(ffma2(pack2(s[j + 2], s[j + 3]), c2, nm2), t2, t3);
@@ -67,7 +78,7 @@ __device__ __forceinline__ void body(const float* s, uint32_t* pr, uint64_t c2, 
   }
   float a0, a1, a2, a3; unpack2(acc0, a0, a1); unpack2(acc1, a2, a3);
   sum += (a0 + a1) + (a2 + a3);
-  m_half = fmaxf(mx0, mx1);
+  if (!SPLIT) m_half = fmaxf(mx0, mx1);
 }
 
 __host__ __device__ constexpr uint32_t rotl8(uint32_t m, int r) { return ((m << (r & 7)) | (m >> ((8 - r) & 7))) & 0xFFu; }
@@ -76,13 +87,18 @@ __host__ __device__ constexpr uint32_t rotl8(uint32_t m, int r) { return ((m << 
 template <int NW, uint32_t MASK, int ROWSUM, int ORDERED, int XCHG>
 __global__ void __launch_bounds__(NW * 32 + 128, 1) k(int iters, unsigned long long* res, float* sink, int with_mma) {
   constexpr int COLS = 176 / (NW / 4);
-  constexpr int kRegsSoftmax = NW == 8 ? 216 : 112, kRegsOther = NW == 8 ? 72 : 56;
+  constexpr int kRegsSoftmax = NW == 8 ? 216 : 112, kRegsOther = NW == 8 ? 72 : 32;   // setmaxnreg only redistributes the launch allocation (640 x 96 = 16 x 32 x 112 + 4 x 32 x 32)
   constexpr int G = NW / 4;   // warps per row group (= per SM sub-partition)
   extern __shared__ uint8_t smem_raw[];
   __shared__ int done_warps;
   __shared__ uint32_t tmem_slot;
   __shared__ float xchg[2][G][128];
-  if (threadIdx.x == 0) done_warps = 0;
+  __shared__ __align__(8) uint64_t xbar[4][2];          // XCHG == 2: one mbarrier per row group and tile parity, G arrivals
+  if (threadIdx.x == 0) {
+    done_warps = 0;
+    for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&xbar[i >> 1][i & 1]), G);
+    fence_mbar_init();
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0) { tmem_alloc(smem_u32(&tmem_slot), 512); tmem_relinquish(); }
   tc_fence_before(); __syncthreads(); tc_fence_after();
@@ -129,14 +145,27 @@ __global__ void __launch_bounds__(NW * 32 + 128, 1) k(int iters, unsigned long l
       uint32_t pr[COLS / 2];
       float m_half, sum = 0.f;
       // four staggered masks, one per warp of the sub-partition
-      if (g == 0) body<COLS, rotl8(MASK, 0), ROWSUM, ORDERED>(s, pr, c2, nm2, m_half, sum);
-      else if (g == 1) body<COLS, rotl8(MASK, G == 2 ? 2 : 1), ROWSUM, ORDERED>(s, pr, c2, nm2, m_half, sum);
-      else if (g == 2) body<COLS, rotl8(MASK, 2), ROWSUM, ORDERED>(s, pr, c2, nm2, m_half, sum);
-      else body<COLS, rotl8(MASK, 3), ROWSUM, ORDERED>(s, pr, c2, nm2, m_half, sum);
+      const uint32_t xb = smem_u32(&xbar[r][it & 1]);
+      auto post = [&](float mh) {
+        if (XCHG == 2) {
+          xchg[it & 1][g][row] = mh;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(xb);
+        }
+      };
+      if (g == 0) body<COLS, rotl8(MASK, 0), ROWSUM, ORDERED, XCHG == 2>(s, pr, c2, nm2, m_half, sum, post);
+      else if (g == 1) body<COLS, rotl8(MASK, G == 2 ? 2 : 1), ROWSUM, ORDERED, XCHG == 2>(s, pr, c2, nm2, m_half, sum, post);
+      else if (g == 2) body<COLS, rotl8(MASK, 2), ROWSUM, ORDERED, XCHG == 2>(s, pr, c2, nm2, m_half, sum, post);
+      else body<COLS, rotl8(MASK, 3), ROWSUM, ORDERED, XCHG == 2>(s, pr, c2, nm2, m_half, sum, post);
       float m_loc = m_half;
-      if (XCHG) {
+      if (XCHG == 1) {
         xchg[it & 1][g][row] = m_half;
         named_bar_sync(1 + r, G * 32);
+#pragma unroll
+        for (int o = 1; o < G; ++o) m_loc = fmaxf(m_loc, xchg[it & 1][(g + o) % G][row]);
+      }
+      if (XCHG == 2) {
+        mbar_wait(xb, (it >> 1) & 1);
 #pragma unroll
         for (int o = 1; o < G; ++o) m_loc = fmaxf(m_loc, xchg[it & 1][(g + o) % G][row]);
       }
@@ -189,27 +218,132 @@ void run(const char* name, int iters) {
   fflush(stdout);
 }
 
+
+// Ping-pong organisation probe: ONE warp per SM sub-partition (4 warps), a thread owns a whole 176-column row and walks
+// it as two chunks of 88 columns (no exchange of partial row maxima at all).  How long is one tile with the
+// sub-partition to itself?  (TEAMS = 2: a second team of 4 warps does the same on another buffer, half a tile out of phase.)
+template <uint32_t MASK, int ROWSUM, int TEAMS>
+__global__ void __launch_bounds__(TEAMS * 128 + 128, 1) kpp(int iters, unsigned long long* res, float* sink, int with_mma) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ int done_warps;
+  __shared__ uint32_t tmem_slot;
+  if (threadIdx.x == 0) done_warps = 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) { tmem_alloc(smem_u32(&tmem_slot), 512); tmem_relinquish(); }
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tm = tmem_slot;
+  constexpr int NWS = TEAMS * 4;
+  if (warp >= NWS) {
+    setmaxnreg_dec<72>();
+    if (warp == NWS && with_mma && lane == 0) {
+      uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+      const uint32_t sb = smem_u32(smem);
+      const uint64_t qd = make_smem_desc_sw128(sb, 16, 1024), kd = make_smem_desc_sw128(sb + 32768, 16, 1024);
+      const uint64_t vd = make_smem_desc_sw128(sb + 32768 + 45056, 176 * 128, 1024);
+      constexpr uint32_t idQK = make_idesc_bf16(128, 160, 0), idPV = make_idesc_bf16(128, 128, 1);   // N = 160: D stays inside columns 352..511
+      long long n = 0;
+      while (*reinterpret_cast<volatile int*>(&done_warps) < NWS) {
+        for (int j = 0; j < 8; ++j) umma_ss(tm + 352, qd + ((((j >> 2) * 16384 + (j & 3) * 32)) >> 4), kd + ((((j >> 2) * 22528 + (j & 3) * 32)) >> 4), idQK, j > 0);
+        for (int j = 0; j < 11; ++j) umma_ts(tm + 352, tm + 352 + j * 8, vd + ((j * 16 * 128) >> 4), idPV, 1);
+        ++n;
+      }
+      res[148 * 32 + blockIdx.x] = (unsigned long long)n;
+    }
+  } else {
+    setmaxnreg_inc<TEAMS == 1 ? 216 : 216>();
+    const int r = warp & 3, team = warp >> 2;
+    const uint32_t lane_field = (uint32_t)(r * 32) << 16;
+    const uint32_t s_addr = tm + lane_field + team * 176;
+    const uint32_t p_addr = s_addr;      // P over the first 88 columns of the team's own S buffer (re-initialised below)
+    uint32_t z[32]; for (int j = 0; j < 32; ++j) z[j] = __float_as_uint(-1.0f - 0.01f * j);
+    auto reinit = [&]() { for (int c0 = 0; c0 < 96; c0 += 32) tmem_st_x32(s_addr + c0, z); };
+    for (int c0 = 0; c0 + 32 <= 176; c0 += 32) tmem_st_x32(s_addr + c0, z);
+    tmem_st_x16(s_addr + 160, z); tmem_wait_st();
+    __syncwarp();
+    const float c = 0.1275f;
+    float m_ref = 0.3f, l_run = 0.f, m_true = -1e30f;
+    const uint64_t c2 = pack2(c, c);
+    float s[88]; uint32_t* sr = reinterpret_cast<uint32_t*>(s);
+    if (team == 1) { for (int w = 0; w < 40; ++w) l_run += ex2_approx(l_run * 1e-20f - w); }   // some phase offset
+    ld_cols<88>(s_addr, sr);
+    const long long t0 = clock64();
+    auto nopost = [](float) {};
+    for (int it = 0; it < iters; ++it) {
+      const float neg = -m_ref * c;
+      const uint64_t nm2 = pack2(neg, neg);
+      uint32_t pr[88];
+      float mh0, mh1, sum = 0.f;
+      tmem_wait_ld();
+      body<88, MASK, ROWSUM, 1, 0>(s, pr, c2, nm2, mh0, sum, nopost);
+      ld_cols<88>(s_addr + 88, sr);
+      tmem_wait_ld();
+      body<88, rotl8(MASK, 2), ROWSUM, 1, 0>(s, pr + 44, c2, nm2, mh1, sum, nopost);
+      const float m_loc = fmaxf(mh0, mh1);
+      const bool exact = __any_sync(0xffffffffu, !((m_loc - m_ref) * c <= 8.0f));
+      if (exact) m_ref = m_loc;
+      l_run += sum;
+      m_true = fmaxf(m_true, m_loc);
+      tmem_st_x32(p_addr, pr); tmem_st_x32(p_addr + 32, pr + 32); tmem_st_x16(p_addr + 64, pr + 64); tmem_st_x8(p_addr + 80, pr + 80);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      reinit();                      // stands in for the next QK^T writing S (keeps the values finite)
+      tmem_wait_st();
+      ld_cols<88>(s_addr, sr);
+    }
+    tmem_wait_ld();
+    const long long t1 = clock64();
+    if (lane == 0) { res[blockIdx.x * 32 + warp] = (unsigned long long)(t1 - t0); atomicAdd(&done_warps, 1); }
+    __syncwarp();
+    sink[blockIdx.x * 512 + threadIdx.x] = l_run + m_true + s[0];
+  }
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  if (warp == 0) tmem_dealloc(tm, 512);
+}
+
+template <uint32_t MASK, int ROWSUM, int TEAMS>
+void runpp(const char* name, int iters) {
+  const int SM = 200 * 1024;
+  auto fn = kpp<MASK, ROWSUM, TEAMS>;
+  cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);
+  double out[2] = {0, 0};
+  for (int with_mma = 0; with_mma < 2; ++with_mma) {
+    cudaMemset(d_res, 0, (148 * 32 + 148) * 8);
+    fn<<<148, TEAMS * 128 + 128, SM>>>(iters, d_res, d_sink, with_mma);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("%s: err %s\n", name, cudaGetErrorString(e)); exit(1); }
+    std::vector<unsigned long long> h(148 * 32 + 148);
+    cudaMemcpy(h.data(), d_res, h.size() * 8, cudaMemcpyDeviceToHost);
+    double mx = 0; for (int i = 0; i < 148 * 32; ++i) mx = h[i] > mx ? (double)h[i] : mx;
+    out[with_mma] = mx / iters;
+  }
+  printf("%-64s           %7.1f clk per tile per team alone   %7.1f with MMA stream\n", name, out[0], out[1]);
+  fflush(stdout);
+}
+
 int main(int argc, char** argv) {
   const int iters = argc > 1 ? atoi(argv[1]) : 3000;
   cudaMalloc(&d_res, (148 * 32 + 148) * 8); cudaMalloc(&d_sink, 148 * 512 * 4);
-  //                 NW  MASK  ROWSUM ORDERED XCHG
-  run<8, 0x11u, 1, 1, 1>(" 8 warps x 88, poly 2/8, rowsum, ordered, xchg   (round-1 kernel)", iters);
-  run<8, 0x11u, 1, 0, 1>(" 8 warps x 88, poly 2/8, rowsum, unordered, xchg", iters);
-  run<8, 0x11u, 1, 1, 0>(" 8 warps x 88, poly 2/8, rowsum, ordered, no xchg", iters);
-  run<8, 0x11u, 0, 1, 1>(" 8 warps x 88, poly 2/8, no rowsum, ordered, xchg", iters);
-  run<8, 0x49u, 1, 1, 1>(" 8 warps x 88, poly 3/8, rowsum, ordered, xchg", iters);
-  run<8, 0x49u, 0, 1, 1>(" 8 warps x 88, poly 3/8, no rowsum, ordered, xchg", iters);
-  run<8, 0x55u, 0, 1, 1>(" 8 warps x 88, poly 4/8, no rowsum, ordered, xchg", iters);
-  run<8, 0x00u, 1, 1, 1>(" 8 warps x 88, poly 0/8, rowsum, ordered, xchg", iters);
-  run<16, 0x11u, 1, 1, 1>("16 warps x 44, poly 2/8, rowsum, ordered, xchg", iters);
-  run<16, 0x11u, 1, 0, 1>("16 warps x 44, poly 2/8, rowsum, unordered, xchg", iters);
-  run<16, 0x11u, 1, 1, 0>("16 warps x 44, poly 2/8, rowsum, ordered, no xchg", iters);
-  run<16, 0x11u, 0, 1, 1>("16 warps x 44, poly 2/8, no rowsum, ordered, xchg", iters);
-  run<16, 0x49u, 1, 1, 1>("16 warps x 44, poly 3/8, rowsum, ordered, xchg", iters);
-  run<16, 0x49u, 0, 1, 1>("16 warps x 44, poly 3/8, no rowsum, ordered, xchg", iters);
-  run<16, 0x49u, 0, 0, 1>("16 warps x 44, poly 3/8, no rowsum, unordered, xchg", iters);
-  run<16, 0x55u, 0, 1, 1>("16 warps x 44, poly 4/8, no rowsum, ordered, xchg", iters);
-  run<16, 0x55u, 1, 1, 1>("16 warps x 44, poly 4/8, rowsum, ordered, xchg", iters);
-  run<16, 0x00u, 1, 1, 1>("16 warps x 44, poly 0/8, rowsum, ordered, xchg", iters);
+  runpp<0x11u, 1, 1>("PP: 4 warps (1 per SMSP) x 176 cols, poly 2/8, rowsum (one team alone; includes a 96-col TMEM re-init)", iters);
+  runpp<0x11u, 1, 2>("PP: 2 teams x 4 warps x 176 cols, poly 2/8, rowsum (per team; includes a 96-col TMEM re-init)", iters);
+  runpp<0x49u, 1, 1>("PP: 4 warps x 176 cols, poly 3/8, rowsum", iters);
+  runpp<0x49u, 1, 2>("PP: 2 teams, poly 3/8, rowsum", iters);
+  runpp<0x55u, 1, 1>("PP: 4 warps x 176 cols, poly 4/8, rowsum", iters);
+  runpp<0x00u, 1, 1>("PP: 4 warps x 176 cols, poly 0/8, rowsum", iters);
+  //                 NW  MASK  ROWSUM ORDERED XCHG(0 none, 1 bar.sync at the end, 2 post at the midpoint + mbarrier wait at the end)
+  run<16, 0x11u, 1, 1, 1>("16 warps x 44, poly 2/8, rowsum, bar.sync xchg", iters);
+  run<16, 0x11u, 1, 1, 2>("16 warps x 44, poly 2/8, rowsum, split mbarrier xchg", iters);
+  run<16, 0x11u, 1, 1, 0>("16 warps x 44, poly 2/8, rowsum, no xchg", iters);
+  run<16, 0x11u, 0, 1, 2>("16 warps x 44, poly 2/8, no rowsum, split mbarrier xchg", iters);
+  run<16, 0x49u, 1, 1, 2>("16 warps x 44, poly 3/8, rowsum, split mbarrier xchg", iters);
+  run<16, 0x49u, 0, 1, 2>("16 warps x 44, poly 3/8, no rowsum, split mbarrier xchg", iters);
+  run<16, 0x55u, 1, 1, 2>("16 warps x 44, poly 4/8, rowsum, split mbarrier xchg", iters);
+  run<16, 0x00u, 1, 1, 2>("16 warps x 44, poly 0/8, rowsum, split mbarrier xchg", iters);
+  run<16, 0x11u, 1, 0, 2>("16 warps x 44, poly 2/8, rowsum, unordered, split mbarrier xchg", iters);
+  run<8, 0x11u, 1, 1, 1>(" 8 warps x 88, poly 2/8, rowsum, bar.sync xchg   (round-1 kernel)", iters);
+  run<8, 0x11u, 1, 1, 2>(" 8 warps x 88, poly 2/8, rowsum, split mbarrier xchg", iters);
+  run<8, 0x49u, 1, 1, 2>(" 8 warps x 88, poly 3/8, rowsum, split mbarrier xchg", iters);
+  run<8, 0x11u, 0, 1, 2>(" 8 warps x 88, poly 2/8, no rowsum, split mbarrier xchg", iters);
+  run<8, 0x49u, 0, 1, 2>(" 8 warps x 88, poly 3/8, no rowsum, split mbarrier xchg", iters);
   return 0;
 }

@@ -25,7 +25,7 @@ extern "C" {
 #define LA_ERR_UNSUPPORTED (-2) /* valid for the reference but not built here (e.g. head_dim != 128) */
 #define LA_ERR_CUDA (-3)        /* CUDA driver / runtime error, see la_last_error()                  */
 
-#define LA_ABI_VERSION 3   /* 2: la_fwd_params.out_is_f32, la_rope_cast_sm100; 3: la_combine_params dtypes, la_fwd_params.sched */
+#define LA_ABI_VERSION 3   /* 2: la_fwd_params.out_is_f32, la_rope_cast_sm100; 3: la_combine_params dtypes, la_list_pack/unpack_sm100 */
 
 /* Tile geometry of the skip list.  API-visible: mirrors tile_size_fwd_sm90
  * (hopper/_internal/cpp/tile_size.h:10-62) == LiteAttention.get_MN (hopper/lite_attention.py:87-111).
@@ -138,6 +138,15 @@ int la_combine_sm100(const la_combine_params* p, void* stream);
 
 /* Fused 3-D RoPE + bf16 cast (HBM-bound elementwise kernel). */
 int la_rope_cast_sm100(const la_rope_params* p, void* stream);
+
+/* Compact resident skip state (the reference keeps int32 [2, max_batch, H, qtiles, ktiles+1] per layer
+ * object, hopper/lite_attention.py:113-153): two bits per (row, K tile) -- "listed" and "a range starts here" --
+ * uint32 bits[rows][2][ceil(ktiles/32)].  pack: int32 list rows -> bits (rows whose ranges are not descending and
+ * disjoint cannot be represented: they are zeroed and counted in *bad_rows, which may be NULL); unpack: bits -> rows
+ * [len, s0, e0, ...] (entries past len untouched).  unpack(pack(row)) == row on [0, len] for every row the update
+ * kernel writes. */
+int la_list_pack_sm100(const int32_t* list, uint32_t* bits, int64_t rows, int ktiles, int32_t* bad_rows, void* stream);
+int la_list_unpack_sm100(const uint32_t* bits, int32_t* list, int64_t rows, int ktiles, void* stream);
 
 /* Number of kernels launched through this library by the calling process (for bench accounting). */
 uint64_t la_launch_count(void);

@@ -57,7 +57,8 @@ class RopeParams(ctypes.Structure):
 _lib = None
 
 EXPORTS = ("la_abi_version", "la_last_error", "la_get_tile_mn", "la_fwd_sm100", "la_skip_update_sm100",
-           "la_fwd_skip_sm100", "la_combine_sm100", "la_rope_cast_sm100", "la_launch_count")
+           "la_fwd_skip_sm100", "la_combine_sm100", "la_rope_cast_sm100", "la_launch_count", "la_list_pack_sm100",
+           "la_list_unpack_sm100")
 
 
 def lib():
@@ -80,6 +81,9 @@ def lib():
         L.la_combine_sm100.argtypes = [ctypes.POINTER(CombineParams), _c_vp]
         L.la_rope_cast_sm100.argtypes = [ctypes.POINTER(RopeParams), _c_vp]
         L.la_watchdog_read.argtypes = [ctypes.POINTER(ctypes.c_uint * 4)]
+        if hasattr(L, "la_list_pack_sm100"):
+            L.la_list_pack_sm100.argtypes = [_c_vp, _c_vp, _c_i64, ctypes.c_int, _c_vp, _c_vp]
+            L.la_list_unpack_sm100.argtypes = [_c_vp, _c_vp, _c_i64, ctypes.c_int, _c_vp]
         # LITEATTN_B200_LIB builds of older revisions (tools/ab.py) share the forward / update structs
         if L.la_abi_version() != 3 and not os.environ.get("LITEATTN_B200_LIB"):
             raise RuntimeError("libliteattn_b200.so ABI version mismatch")
@@ -193,6 +197,24 @@ def combine(o_parts, lse_parts, out, lse):
     c.out_is_f32 = int(out.dtype == torch.float32)
     with torch.cuda.device(out.device):
         _check(lib().la_combine_sm100(ctypes.byref(c), _stream(out.device)), "la_combine_sm100")
+
+
+def list_pack(lists, bits, bad_rows=None):
+    """la_list_pack_sm100: int32 rows [..., ktiles+1] (contiguous) -> uint32 bits [rows, 2, ceil(ktiles/32)] (as int32 storage)."""
+    ktiles = lists.shape[-1] - 1
+    rows = lists.numel() // (ktiles + 1)
+    with torch.cuda.device(lists.device):
+        _check(lib().la_list_pack_sm100(_ptr(lists), _ptr(bits), rows, ktiles, _ptr(bad_rows), _stream(lists.device)),
+               "la_list_pack_sm100")
+
+
+def list_unpack(bits, lists):
+    """la_list_unpack_sm100: bits [rows, 2, words] -> int32 rows [..., ktiles+1] (entries past len untouched)."""
+    ktiles = lists.shape[-1] - 1
+    rows = lists.numel() // (ktiles + 1)
+    with torch.cuda.device(lists.device):
+        _check(lib().la_list_unpack_sm100(_ptr(bits), _ptr(lists), rows, ktiles, _stream(lists.device)),
+               "la_list_unpack_sm100")
 
 
 def launch_count():

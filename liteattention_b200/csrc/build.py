@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libliteattn_b200.so")
 SOURCES = ["la_all.cu"]
-DEPS = ["la_all.cu", "la_fwd_sm100.cu", "la_skip_update.cu", "la_combine.cu", "la_rope_cast.cu", "la_api.cu", "la_ptx.cuh",
+DEPS = ["la_all.cu", "la_fwd_sm100.cu", "la_skip_update.cu", "la_combine.cu", "la_rope_cast.cu", "la_list_codec.cu", "la_api.cu", "la_ptx.cuh",
         "la_tmem_ptx.cuh", "la_kernels.h", os.path.join("..", "..", "include", "liteattn_b200.h")]
 
 

@@ -5,4 +5,5 @@
 #include "la_skip_update.cu"
 #include "la_combine.cu"
 #include "la_rope_cast.cu"
+#include "la_list_codec.cu"
 #include "la_api.cu"

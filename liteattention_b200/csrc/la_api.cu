@@ -284,6 +284,26 @@ int la_fwd_skip_sm100(const la_fwd_params* fwd, const la_update_params* upd, voi
   return la_skip_update_sm100(&u, stream);
 }
 
+int la_list_pack_sm100(const int32_t* list, uint32_t* bits, int64_t rows, int ktiles, int32_t* bad_rows, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  LA_CHECK_ARG(list && bits && rows > 0 && rows < (1ll << 31) && ktiles > 0, "la_list_pack_sm100: bad arguments");
+  if (ktiles > la::kFwdMaxTiles) return fail(LA_ERR_UNSUPPORTED, "la_list_pack_sm100: ktiles %d > %d", ktiles, la::kFwdMaxTiles);
+  la::la_list_pack_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, stream>>>(list, bits, (int)rows, ktiles, bad_rows);
+  LA_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return LA_OK;
+}
+
+int la_list_unpack_sm100(const uint32_t* bits, int32_t* list, int64_t rows, int ktiles, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  LA_CHECK_ARG(list && bits && rows > 0 && rows < (1ll << 31) && ktiles > 0, "la_list_unpack_sm100: bad arguments");
+  if (ktiles > la::kFwdMaxTiles) return fail(LA_ERR_UNSUPPORTED, "la_list_unpack_sm100: ktiles %d > %d", ktiles, la::kFwdMaxTiles);
+  la::la_list_unpack_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, stream>>>(bits, list, (int)rows, ktiles);
+  LA_CUDA(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return LA_OK;
+}
+
 int la_combine_sm100(const la_combine_params* p, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   LA_CHECK_ARG(p != nullptr && p->o_parts && p->lse_parts && p->out, "la_combine_sm100: NULL argument");

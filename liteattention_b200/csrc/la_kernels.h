@@ -46,6 +46,9 @@ constexpr int kUpdWarpsPerBlock = 4;
 __global__ void la_skip_update_kernel(const UpdateKernelArgs args);
 size_t la_skip_update_smem_bytes(int ktiles);
 
+__global__ void la_list_pack_kernel(const int32_t* list, uint32_t* bits, int rows, int ktiles, int32_t* bad_rows);
+__global__ void la_list_unpack_kernel(const uint32_t* bits, int32_t* list, int rows, int ktiles);
+
 struct CombineKernelArgs {
   const void* o_parts[8];      // (b, s, h, d) contiguous, bf16 or fp32 (template parameter In)
   const float* lse_parts[8];   // (b, h, s) fp32 contiguous

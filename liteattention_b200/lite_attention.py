@@ -10,7 +10,12 @@ integration) runs unchanged.  Differences, all documented in DESIGN.md:
   * the default (empty) must-do list is not materialised per call (the reference allocates and broadcasts a
     [max_batch,H,qtiles,ktiles+1] tensor every call, :239-241); the kernel treats "no list" as `[2,0,0]`;
   * `calc_percentage` keeps the reference's (broken for descending lists, :61-85) formula for drop-in
-    compatibility; `sparsity()` / `last_sparsity` give the correct figure.
+    compatibility; `sparsity()` / `last_sparsity` give the correct figure;
+  * `compact_state=True` (keyword-only extension, or LITE_ATTENTION_COMPACT_STATE=1; off by default): the resident
+    state is two bits per (row, K tile), allocated for the batch actually seen -- 2.6 MB per layer object at the
+    Wan2.1-14B shape instead of the reference's 326 MB int32 double buffer (:124, max_batch_size 4).  The int32 rows
+    the kernels consume live in a scratch pair shared by all layer objects of a stream; la_list_unpack / la_list_pack
+    (csrc/la_list_codec.cu) convert around every call, losslessly.
 """
 import os
 from typing import Optional, Tuple, Union
@@ -19,6 +24,23 @@ import torch
 
 from . import _native
 from .flash_attn_interface import _flash_attn_forward, flash_attn_func, fwd_peer_scatter
+
+
+_LIST_WS = {}
+
+
+def _list_scratch(device, shape):
+    """(read, write) int32 scratch rows shared by every compact-state LiteAttention object of a device / stream / shape:
+    a call expands its bitmaps into `read`, the kernels write `write`, the object packs `write` back -- all on one
+    stream, so the next object can reuse the pair."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, tuple(shape))
+    ws = _LIST_WS.get(key)
+    if ws is None:
+        if len(_LIST_WS) >= 8:
+            _LIST_WS.clear()
+        ws = _LIST_WS[key] = (torch.zeros(shape, dtype=torch.int32, device=device),
+                              torch.zeros(shape, dtype=torch.int32, device=device))
+    return ws
 
 
 class LiteAttention:
@@ -33,8 +55,12 @@ class LiteAttention:
         max_batch_size: leading dimension the list buffers are allocated for.  Default 4.
     """
 
-    def __init__(self, enable_skipping: bool = True, threshold: float = -10.0, max_batch_size: int = 4):
-        self._skip_list = None
+    def __init__(self, enable_skipping: bool = True, threshold: float = -10.0, max_batch_size: int = 4, *,
+                 compact_state: Optional[bool] = None):
+        self._compact = (os.getenv("LITE_ATTENTION_COMPACT_STATE", "0") not in ("0", "", "FALSE", "false")
+                         if compact_state is None else bool(compact_state))
+        self._bits = None          # compact mode: int32-typed storage of uint32 [batch, H, qtiles, 2, words]
+        self._skip_list_buf = None
         self._phase = 0
 
         self._last_seq_len = None
@@ -51,6 +77,47 @@ class LiteAttention:
         self.enable_skipping = enable_skipping
         self.set_threshold(threshold)
         self.max_batch_size = max_batch_size
+
+    # ------------------------------------------------------------------ state
+    @property
+    def _skip_list(self):
+        """[2, batch, H, qtiles, ktiles+1] int32, like the reference's attribute.  In compact mode it is exported on
+        demand from the bitmaps and both halves hold the list the next call will read."""
+        if self._compact:
+            if self._bits is None:
+                return None
+            cur = self._export_lists()
+            return torch.stack([cur, cur])
+        return self._skip_list_buf
+
+    @_skip_list.setter
+    def _skip_list(self, value):
+        if self._compact and value is not None:
+            lists = value[self._phase] if value.dim() == 5 else value
+            self._import_lists(lists.contiguous())
+        elif self._compact:
+            self._bits = None
+        else:
+            self._skip_list_buf = value
+
+    def _export_lists(self, batch: Optional[int] = None):
+        b = self._bits.shape[0] if batch is None else batch
+        h, qt, kt = self._bits.shape[1], self._bits.shape[2], self._ktiles
+        out = torch.zeros(b, h, qt, kt + 1, dtype=torch.int32, device=self._bits.device)
+        _native.list_unpack(self._bits[:b], out)
+        return out
+
+    def _import_lists(self, lists: torch.Tensor):
+        """Pack int32 rows [batch, H, qtiles, ktiles+1] into the resident bitmaps (rows must be descending/disjoint)."""
+        b, h, qt, kp1 = lists.shape
+        words = (kp1 - 1 + 31) // 32
+        bits = torch.empty(b, h, qt, 2, words, dtype=torch.int32, device=lists.device)
+        bad = torch.zeros(1, dtype=torch.int32, device=lists.device)
+        _native.list_pack(lists, bits, bad)
+        if int(bad.item()) != 0:
+            raise ValueError("compact_state: the skip list has rows that are not descending, disjoint ranges; "
+                             "use compact_state=False for hand-made lists")
+        self._bits, self._ktiles, self._qtiles = bits, kp1 - 1, qt
 
     # ------------------------------------------------------------------ static helpers (reference API)
     @staticmethod
@@ -161,11 +228,20 @@ class LiteAttention:
         current_num_heads = query.shape[2]
         v_colmajor = value.shape[-3] == head_dim
         dtype, device = query.dtype, query.device
-        if (self._skip_list is None or self._last_seq_len != current_seq_len
-                or self._skip_list.device != query.device or self._last_head_dim != head_dim
+        state = self._bits if self._compact else self._skip_list_buf
+        if (state is None or self._last_seq_len != current_seq_len
+                or state.device != query.device or self._last_head_dim != head_dim
                 or self._last_v_colmajor != v_colmajor or self._last_dtype != dtype
                 or self._last_device != device or self._last_num_heads != current_num_heads):
-            self._skip_list = self._init_skip_list(query, value, must_skip_list)
+            if self._compact:
+                batch, seq_len, heads, _ = query.shape
+                assert batch <= self.max_batch_size, \
+                    "batch size must be less than or equal to max_batch_size (modify max_batch_size in LiteAttention constructor)"
+                # allocated for the batch actually seen (grown on demand below), not for max_batch_size
+                self._import_lists(LiteAttention.init_skip_list(batch, seq_len, heads, head_dim, v_colmajor, dtype, device,
+                                                                must_skip_list)[0])
+            else:
+                self._skip_list_buf = self._init_skip_list(query, value, must_skip_list)
             self._phase = 0
             self._last_seq_len = current_seq_len
             self._last_head_dim = head_dim
@@ -175,11 +251,25 @@ class LiteAttention:
             self._last_num_heads = current_num_heads
             if os.getenv("LITE_ATTENTION_VERBOSE", "FALSE") != "FALSE":
                 print("[Warning]: reinitialized skip list during the forward pass")
+        if self._compact:
+            batch = query.shape[0]
+            assert batch <= self.max_batch_size, \
+                "batch size must be less than or equal to max_batch_size (modify max_batch_size in LiteAttention constructor)"
+            if batch > self._bits.shape[0]:        # new batch rows start from the dense initial list
+                extra = LiteAttention.init_skip_list(batch - self._bits.shape[0], current_seq_len, current_num_heads, head_dim,
+                                                     v_colmajor, dtype, device)[0]
+                old = self._bits
+                self._import_lists(extra)
+                self._bits = torch.cat([old, self._bits])
+            read_list, write_list = _list_scratch(query.device, (batch,) + tuple(self._bits.shape[1:3]) + (self._ktiles + 1,))
+            _native.list_unpack(self._bits[:batch], read_list)
+            self._phase ^= 1
+            return read_list, write_list
         if self._phase == 0:
-            read_list, write_list = self._skip_list[0], self._skip_list[1]
+            read_list, write_list = self._skip_list_buf[0], self._skip_list_buf[1]
             self._phase = 1
         else:
-            read_list, write_list = self._skip_list[1], self._skip_list[0]
+            read_list, write_list = self._skip_list_buf[1], self._skip_list_buf[0]
             self._phase = 0
         return read_list, write_list
 
@@ -244,6 +334,8 @@ class LiteAttention:
                 thr=self.threshold)
             output = (o, lse) if return_softmax_lse else o
 
+        if self._compact and write_list is not None:
+            _native.list_pack(write_list, self._bits[:query.shape[0]])      # the list the next call will read
         if self.enable_skipping and os.getenv("LITE_ATTENTION_VERBOSE", "FALSE") != "FALSE":
             real_batch_size = query.shape[0]
             self._last_percentage = 1.0 - LiteAttention.sparsity(read_list[:real_batch_size])
@@ -253,13 +345,15 @@ class LiteAttention:
     @property
     def read_list(self) -> Optional[torch.Tensor]:
         """The list the NEXT call will read (i.e. the one the last call wrote)."""
-        if self._skip_list is None:
+        if self._compact:
+            return None if self._bits is None else self._export_lists()
+        if self._skip_list_buf is None:
             return None
-        return self._skip_list[self._phase]
+        return self._skip_list_buf[self._phase]
 
     def last_sparsity(self, batch: Optional[int] = None) -> float:
         """Sparsity of the list the next call will use."""
-        if self._skip_list is None:
+        if (self._bits if self._compact else self._skip_list_buf) is None:
             return 0.0
         rl = self.read_list
         return LiteAttention.sparsity(rl if batch is None else rl[:batch])
@@ -268,11 +362,14 @@ class LiteAttention:
         """Extension (not in the reference): start from a given list instead of the dense initial one, e.g. a list
         exported from an earlier run or synthesised at a target sparsity.  skip_list: int32
         [batch <= max_batch_size, heads, qtiles, ktiles+1] for the geometry of `query`."""
-        buf = self._init_skip_list(query, value)
-        assert skip_list.shape[1:] == buf.shape[2:] and skip_list.shape[0] <= buf.shape[1], \
-            f"skip_list shape {tuple(skip_list.shape)} does not match {tuple(buf.shape[1:])}"
-        buf[:, :skip_list.shape[0]] = skip_list.to(device=buf.device, dtype=torch.int32)
-        self._skip_list = buf
+        if self._compact:
+            self._import_lists(skip_list.to(device=query.device, dtype=torch.int32).contiguous())
+        else:
+            buf = self._init_skip_list(query, value)
+            assert skip_list.shape[1:] == buf.shape[2:] and skip_list.shape[0] <= buf.shape[1], \
+                f"skip_list shape {tuple(skip_list.shape)} does not match {tuple(buf.shape[1:])}"
+            buf[:, :skip_list.shape[0]] = skip_list.to(device=buf.device, dtype=torch.int32)
+            self._skip_list_buf = buf
         self._phase = 0
         self._last_seq_len = query.shape[1]
         self._last_head_dim = query.shape[-1]
@@ -283,7 +380,8 @@ class LiteAttention:
 
     def reset_skip_state(self):
         """Forget the skip lists (next call starts dense).  hopper/lite_attention.py:293-304."""
-        self._skip_list = None
+        self._skip_list_buf = None
+        self._bits = None
         self._phase = 0
         self._last_seq_len = None
         self._last_head_dim = None

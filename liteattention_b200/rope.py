@@ -5,25 +5,42 @@ runs in front of every LiteAttention call (reference README.md:301-315),
 
 as ONE HBM pass (`la_rope_cast_sm100`, liteattention_b200/csrc/la_rope_cast.cu) instead of the float64 complex
 round trip of Wan2.1's `rope_apply` (wan/modules/model.py).  Same arguments as that function."""
+import weakref
 from typing import Dict, Tuple
 
 import torch
 
 from . import _native
 
-_TABLES: Dict[Tuple[int, torch.device], torch.Tensor] = {}
+# (id of the freqs tensor, device) -> (weakref to that tensor, its _version when the table was built, table).  Keyed on
+# the tensor OBJECT, not its address: a freed-and-reallocated or in-place modified `freqs` never meets a stale table,
+# and entries die with their tensors.
+_TABLES: Dict[Tuple[int, torch.device], tuple] = {}
+# id of a grid_sizes tensor -> (weakref, _version, max grid extent): avoids a device sync per call when grid_sizes lives on the GPU
+_GRID_MAX: Dict[int, tuple] = {}
 
 
 def _cos_sin_table(freqs: torch.Tensor, device: torch.device) -> torch.Tensor:
     """freqs: complex [max_pos, d/2] as built by the Wan model (frames | height | width tables concatenated along
-    dim 1) -> fp32 [max_pos, d/2, 2] (cos, sin) on `device`, cached per (tensor, device)."""
-    key = (freqs.data_ptr(), device)
-    t = _TABLES.get(key)
-    if t is None or t.shape[:2] != freqs.shape:
-        f = freqs.to(torch.complex128)
-        t = torch.stack([f.real, f.imag], dim=-1).to(torch.float32).to(device).contiguous()
-        _TABLES[key] = t
+    dim 1) -> fp32 [max_pos, d/2, 2] (cos, sin) on `device`, cached per (tensor object, version, device)."""
+    key = (id(freqs), device)
+    ent = _TABLES.get(key)
+    if ent is not None and ent[0]() is freqs and ent[1] == freqs._version:
+        return ent[2]
+    f = freqs.to(torch.complex128)
+    t = torch.stack([f.real, f.imag], dim=-1).to(torch.float32).to(device).contiguous()
+    _TABLES[key] = (weakref.ref(freqs, lambda _r, k=key: _TABLES.pop(k, None)), freqs._version, t)
     return t
+
+
+def _grid_max(grid_sizes: torch.Tensor) -> int:
+    key = id(grid_sizes)
+    ent = _GRID_MAX.get(key)
+    if ent is not None and ent[0]() is grid_sizes and ent[1] == grid_sizes._version:
+        return ent[2]
+    m = int(grid_sizes.max().item()) if grid_sizes.numel() else 0
+    _GRID_MAX[key] = (weakref.ref(grid_sizes, lambda _r, k=key: _GRID_MAX.pop(k, None)), grid_sizes._version, m)
+    return m
 
 
 def rope_apply_bf16(x: torch.Tensor, grid_sizes: torch.Tensor, freqs: torch.Tensor) -> torch.Tensor:
@@ -41,8 +58,7 @@ def rope_apply_bf16(x: torch.Tensor, grid_sizes: torch.Tensor, freqs: torch.Tens
     if x.stride(-1) != 1 or x.data_ptr() % 16 or any((st * elt) % 16 for st in x.stride()[:3]):
         x = x.contiguous()
     grid = grid_sizes.to(device=x.device, dtype=torch.int32).contiguous()
-    gmax = grid_sizes.max(dim=0).values.tolist() if grid_sizes.numel() else [0, 0, 0]
-    if max(gmax) > freqs.shape[0]:
+    if _grid_max(grid_sizes) > freqs.shape[0]:
         raise ValueError("rope_apply_bf16: a grid dimension exceeds the position table")
     out = torch.empty((b, s, h, d), dtype=torch.bfloat16, device=x.device)
     _native.rope_cast(x, out, _cos_sin_table(freqs, x.device), grid)

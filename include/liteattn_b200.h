@@ -148,6 +148,14 @@ int la_rope_cast_sm100(const la_rope_params* p, void* stream);
 int la_list_pack_sm100(const int32_t* list, uint32_t* bits, int64_t rows, int ktiles, int32_t* bad_rows, void* stream);
 int la_list_unpack_sm100(const uint32_t* bits, int32_t* list, int64_t rows, int ktiles, void* stream);
 
+/* Host-resident activations (offloaded pipelines; what the reference's users do with `.cuda()` / `.cpu()` around the
+ * call, hopper README "Quick start"): an asynchronous pitched copy of `rows` rows of `width_bytes` between pinned host
+ * memory and device memory (direction inferred from the pointers), on `stream`.  It lets the host-side mirror move one
+ * HEAD GROUP of a (batch, seq, heads, dim) tensor at a time, so that the forward of group g runs while group g+1 is
+ * still on the wire (liteattention_b200/lite_attention.py: LiteAttention.__call__ on pinned CPU tensors). */
+int la_copy2d_async(void* dst, size_t dst_pitch_bytes, const void* src, size_t src_pitch_bytes, size_t width_bytes,
+                    size_t rows, void* stream);
+
 /* Number of kernels launched through this library by the calling process (for bench accounting). */
 uint64_t la_launch_count(void);
 

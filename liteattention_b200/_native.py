@@ -58,7 +58,7 @@ _lib = None
 
 EXPORTS = ("la_abi_version", "la_last_error", "la_get_tile_mn", "la_fwd_sm100", "la_skip_update_sm100",
            "la_fwd_skip_sm100", "la_combine_sm100", "la_rope_cast_sm100", "la_launch_count", "la_list_pack_sm100",
-           "la_list_unpack_sm100")
+           "la_list_unpack_sm100", "la_copy2d_async")
 
 
 def lib():
@@ -84,6 +84,8 @@ def lib():
         if hasattr(L, "la_list_pack_sm100"):
             L.la_list_pack_sm100.argtypes = [_c_vp, _c_vp, _c_i64, ctypes.c_int, _c_vp, _c_vp]
             L.la_list_unpack_sm100.argtypes = [_c_vp, _c_vp, _c_i64, ctypes.c_int, _c_vp]
+        if hasattr(L, "la_copy2d_async"):
+            L.la_copy2d_async.argtypes = [_c_vp, ctypes.c_size_t, _c_vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, _c_vp]
         # LITEATTN_B200_LIB builds of older revisions (tools/ab.py) share the forward / update structs
         if L.la_abi_version() != 3 and not os.environ.get("LITEATTN_B200_LIB"):
             raise RuntimeError("libliteattn_b200.so ABI version mismatch")
@@ -215,6 +217,19 @@ def list_unpack(bits, lists):
     with torch.cuda.device(lists.device):
         _check(lib().la_list_unpack_sm100(_ptr(bits), _ptr(lists), rows, ktiles, _stream(lists.device)),
                "la_list_unpack_sm100")
+
+
+def copy2d_async(dst, src, col0, ncols, stream):
+    """la_copy2d_async for one column block of two equally shaped contiguous (rows..., cols) tensors, one of them in
+    pinned host memory: elements [..., col0 : col0 + ncols] of `src` -> the same elements of `dst`, on `stream`."""
+    assert dst.shape == src.shape and dst.dtype == src.dtype and dst.is_contiguous() and src.is_contiguous()
+    cols = dst.shape[-1]
+    rows = dst.numel() // cols
+    es = dst.element_size()
+    dev = dst.device if dst.is_cuda else src.device
+    with torch.cuda.device(dev):
+        _check(lib().la_copy2d_async(dst.data_ptr() + col0 * es, cols * es, src.data_ptr() + col0 * es, cols * es,
+                                     ncols * es, rows, stream.cuda_stream), "la_copy2d_async")
 
 
 def launch_count():

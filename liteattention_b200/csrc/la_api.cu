@@ -304,6 +304,13 @@ int la_list_unpack_sm100(const uint32_t* bits, int32_t* list, int64_t rows, int 
   return LA_OK;
 }
 
+int la_copy2d_async(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width, size_t rows, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  LA_CHECK_ARG(dst && src && width > 0 && rows > 0 && dst_pitch >= width && src_pitch >= width, "la_copy2d_async: bad arguments");
+  LA_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width, rows, cudaMemcpyDefault, stream));
+  return LA_OK;
+}
+
 int la_combine_sm100(const la_combine_params* p, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   LA_CHECK_ARG(p != nullptr && p->o_parts && p->lse_parts && p->out, "la_combine_sm100: NULL argument");

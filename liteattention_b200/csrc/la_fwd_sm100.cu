@@ -371,17 +371,26 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       // Optional L2 eviction hints like the reference's (mainloop :1002, :1020 EVICT_LAST on K/V, :1092 EVICT_FIRST on Q):
       // K/V of a head are re-read by its 591 Q tiles out of L2, Q is read once.
 #ifndef LA_L2_HINTS
-#define LA_L2_HINTS 0     // same-box A/B (tools/ab.py, profiles/ab_r2.txt): the hints cost 1 % at the Wan shape; off
+#define LA_L2_HINTS 0     // bit 0: K/V evict_last, bit 1: Q evict_first, bit 2: O stores evict_first
 #endif
-#if LA_L2_HINTS
+#if LA_L2_HINTS & 3
       const uint64_t pol_keep = policy_evict_last(), pol_stream = policy_evict_first();
-#define LA_TMA_LOAD(dst, tm, bar_, c0, c1, c2, c3, pol) tma_load_4d_hint(dst, tm, bar_, c0, c1, c2, c3, pol)
+#endif
+#define LA_TMA_LOAD_PLAIN(dst, tm, bar_, c0, c1, c2, c3, pol) tma_load_4d(dst, tm, bar_, c0, c1, c2, c3)
+#define LA_TMA_LOAD_HINT(dst, tm, bar_, c0, c1, c2, c3, pol) tma_load_4d_hint(dst, tm, bar_, c0, c1, c2, c3, pol)
+#if LA_L2_HINTS & 1
+#define LA_TMA_LOAD_KV LA_TMA_LOAD_HINT
 #else
-#define LA_TMA_LOAD(dst, tm, bar_, c0, c1, c2, c3, pol) tma_load_4d(dst, tm, bar_, c0, c1, c2, c3)
+#define LA_TMA_LOAD_KV LA_TMA_LOAD_PLAIN
+#endif
+#if LA_L2_HINTS & 2
+#define LA_TMA_LOAD_Q LA_TMA_LOAD_HINT
+#else
+#define LA_TMA_LOAD_Q LA_TMA_LOAD_PLAIN
 #endif
       mbar_arrive_expect_tx(bar(kBarQFull), kQBytes);
-      LA_TMA_LOAD(smem_base + kOffQ, &tmap_q, bar(kBarQFull), 0, m_block * kM, head, batch, pol_stream);
-      LA_TMA_LOAD(smem_base + kOffQ + kQBlockBytes, &tmap_q, bar(kBarQFull), 64, m_block * kM, head, batch, pol_stream);
+      LA_TMA_LOAD_Q(smem_base + kOffQ, &tmap_q, bar(kBarQFull), 0, m_block * kM, head, batch, pol_stream);
+      LA_TMA_LOAD_Q(smem_base + kOffQ + kQBlockBytes, &tmap_q, bar(kBarQFull), 64, m_block * kM, head, batch, pol_stream);
 
       LA_PROF_DECL(2);
       auto load_kv = [&](const CUtensorMap* tm, uint32_t off, uint32_t full0, uint32_t empty0, int i) {
@@ -399,8 +408,8 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 #endif
         mbar_arrive_expect_tx(bar(full0 + s), kKVBytes);
         const uint32_t dst = smem_base + off + s * kKVBytes;
-        LA_TMA_LOAD(dst, tm, bar(full0 + s), 0, n * kN, head_kv, batch, pol_keep);
-        LA_TMA_LOAD(dst + kKVBlockBytes, tm, bar(full0 + s), 64, n * kN, head_kv, batch, pol_keep);
+        LA_TMA_LOAD_KV(dst, tm, bar(full0 + s), 0, n * kN, head_kv, batch, pol_keep);
+        LA_TMA_LOAD_KV(dst + kKVBlockBytes, tm, bar(full0 + s), 64, n * kN, head_kv, batch, pol_keep);
       };
       load_kv(&tmap_k, kOffK, kBarKFull, kBarKEmpty, 0);
       for (int i = 0; i < T; ++i) {
@@ -790,8 +799,14 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 32; ++j) w[j] = pack_bf16(o[2 * j] * inv, o[2 * j + 1] * inv);
         if (LA_V8_OK) {
+#if LA_L2_HINTS & 4
+          const uint64_t pol_o = policy_evict_first();     // O is written once and not read by this kernel
+#pragma unroll
+          for (int j = 0; j < 4; ++j) stg_v8_hint(obase + o_off + 16 * j, w + 8 * j, pol_o);
+#else
 #pragma unroll
           for (int j = 0; j < 4; ++j) stg_v8(obase + o_off + 16 * j, w + 8 * j);
+#endif
         } else {
           uint4* dst = reinterpret_cast<uint4*>(obase + o_off);
 #pragma unroll

@@ -278,6 +278,11 @@ __device__ __forceinline__ void stg_v8(void* ptr, const uint32_t* r) {
                "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+__device__ __forceinline__ void stg_v8_hint(void* ptr, const uint32_t* r, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;" ::"l"(ptr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "l"(policy)
+               : "memory");
+}
 __device__ __forceinline__ int lds_s32(uint32_t addr) {
   int v;
   asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");

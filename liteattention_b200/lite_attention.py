@@ -16,6 +16,10 @@ integration) runs unchanged.  Differences, all documented in DESIGN.md:
     Wan2.1-14B shape instead of the reference's 326 MB int32 double buffer (:124, max_batch_size 4).  The int32 rows
     the kernels consume live in a scratch pair shared by all layer objects of a stream; la_list_unpack / la_list_pack
     (csrc/la_list_codec.cu) convert around every call, losslessly.
+  * host-resident activations (extension): called with PINNED CPU tensors, the object streams them through the GPU by
+    head groups -- the forward of group g runs while group g+1 is on the wire and group g-1's O is on its way back
+    (la_copy2d_async) -- and returns O in pinned host memory.  There is still no CPU compute path: pageable CPU
+    tensors raise.
 """
 import os
 from typing import Optional, Tuple, Union
@@ -41,6 +45,55 @@ def _list_scratch(device, shape):
         ws = _LIST_WS[key] = (torch.zeros(shape, dtype=torch.int32, device=device),
                               torch.zeros(shape, dtype=torch.int32, device=device))
     return ws
+
+
+class _HostStage:
+    """Device staging for calls on pinned host tensors: two slots of (q, k, v, o) device buffers and of pinned host
+    outputs (call n uses slot n & 1, so its uploads overlap call n-1's compute), one upload and one download stream.
+    Shared by every layer object of a device / shape / dtype."""
+
+    def __init__(self, device, shape, dtype):
+        self.dev = [[torch.empty(shape, dtype=dtype, device=device) for _ in range(4)] for _ in range(2)]
+        self.host_out = [None, None]
+        self.free = [torch.cuda.Event(), torch.cuda.Event()]      # slot reusable: its last download has finished
+        self.h2d = torch.cuda.Stream(device)
+        self.d2h = torch.cuda.Stream(device)
+        self.calls = 0
+
+
+_HOST_STAGES = {}
+
+
+def _host_stage(device, shape, dtype):
+    key = (device.index, tuple(shape), dtype)
+    st = _HOST_STAGES.get(key)
+    if st is None:
+        if len(_HOST_STAGES) >= 2:
+            _HOST_STAGES.clear()
+        st = _HOST_STAGES[key] = _HostStage(device, shape, dtype)
+    return st
+
+
+def host_head_groups(heads: int):
+    """Head-group sizes for streamed host calls: small first and last groups (the first upload and the last download
+    are the only copies nothing overlaps), growing by 2x in between so that a group's upload always finishes under
+    the previous group's compute.  LITE_ATTENTION_HOST_CHUNKS="2,4,8,..." overrides (must sum to `heads`)."""
+    env = os.getenv("LITE_ATTENTION_HOST_CHUNKS", "")
+    if env:
+        sizes = [int(x) for x in env.split(",")]
+        if sum(sizes) != heads or min(sizes) <= 0:
+            raise ValueError(f"LITE_ATTENTION_HOST_CHUNKS={env!r} does not partition {heads} heads")
+        return sizes
+    if heads <= 3:
+        return [heads]
+    last = max(1, heads // 10)
+    sizes, left, nxt = [], heads - last, max(1, heads // 20)
+    while left > 0:
+        g = min(nxt, left, max(1, heads // 3))
+        sizes.append(g)
+        left -= g
+        nxt *= 2
+    return sizes + [last]
 
 
 class LiteAttention:
@@ -308,6 +361,10 @@ class LiteAttention:
         out (extension, keyword-only; the reference's op takes it, `flash_api.cpp:861-870`, its Python does not pass
         it): write the result there instead of allocating -- any device-visible bf16 (batch, seq_len, heads,
         head_dim) buffer, including a peer GPU's memory mapped over NVLink (liteattention_b200/dist.py)."""
+        if query.device.type == "cpu" and query.is_pinned():
+            # host-resident activations: streamed through the GPU by head groups (pageable CPU tensors fall through to
+            # the op, which has no CPU kernel and raises)
+            return self._call_host(query, key, value, scale, return_softmax_lse, must_do_list, must_skip_list, out)
         read_list, write_list = self._get_read_write_lists(query, value, must_skip_list)
 
         must_do_list_expanded = None
@@ -341,6 +398,93 @@ class LiteAttention:
             self._last_percentage = 1.0 - LiteAttention.sparsity(read_list[:real_batch_size])
             print(f"[Info]: Percentage of tiles skipped: {1.0 - self._last_percentage:.2%}")
         return output
+
+    # ------------------------------------------------------------------ call on pinned host tensors
+    def _call_host(self, query, key, value, scale, return_softmax_lse, must_do_list, must_skip_list, out):
+        """query/key/value in PINNED host memory, contiguous (batch, seq_len, heads, head_dim) bf16.  The tensors are
+        streamed through the current CUDA device by head groups; the list handling, kernels and results are those of
+        a device call (same bits).  Returns O in pinned host memory (`out` if given, else one of two internal buffers
+        that alternate between calls) [and softmax_lse on the device].  Everything is asynchronous: call
+        `join_host_copies()` (stream-ordered) or `wait_host_copies()` (blocking) before reading the result on the CPU
+        or overwriting the inputs."""
+        for name, t in (("query", query), ("key", key), ("value", value)):
+            if t.device.type != "cpu" or not t.is_pinned():
+                raise RuntimeError(f"LiteAttention: {name} is a pageable CPU tensor; host-resident inputs must be pinned "
+                                   "(liteattention_b200 computes on the GPU only, there is no CPU path)")
+            if not t.is_contiguous():
+                raise ValueError(f"LiteAttention: host-resident {name} must be contiguous (batch, seq_len, heads, head_dim)")
+        if not (query.shape == key.shape == value.shape) or query.dim() != 4:
+            raise ValueError("LiteAttention: host-resident q, k, v must share one (batch, seq_len, heads, head_dim) shape")
+        if isinstance(out, _native.PeerScatter):
+            raise NotImplementedError("LiteAttention: PeerScatter outputs need device-resident inputs")
+        if not torch.cuda.is_available():
+            raise RuntimeError("LiteAttention: no CUDA device (liteattention_b200 has no CPU path)")
+        device = torch.device("cuda", torch.cuda.current_device())
+        B, S, H, D = query.shape
+        st = _host_stage(device, query.shape, query.dtype)
+        slot = st.calls & 1
+        st.calls += 1
+        dq, dk, dv, do = st.dev[slot]
+        if out is None:
+            if st.host_out[slot] is None:
+                st.host_out[slot] = torch.empty(query.shape, dtype=query.dtype).pin_memory()
+            out = st.host_out[slot]
+        elif (out.device.type != "cpu" or not out.is_pinned() or not out.is_contiguous() or out.shape != query.shape
+              or out.dtype != query.dtype):
+            raise ValueError("LiteAttention: `out` for host-resident inputs must be a pinned contiguous CPU tensor of q's shape")
+
+        read_list, write_list = self._get_read_write_lists(dq, dv, must_skip_list)
+        md = None
+        if self.enable_skipping and must_do_list is not None:
+            md = self._must_do_expanded(must_do_list, write_list.shape, dq, dv)
+        softmax_scale = scale if scale is not None else D ** (-0.5)
+        lse = torch.empty((B, H, S), dtype=torch.float32, device=device) if return_softmax_lse else None
+
+        main = torch.cuda.current_stream(device)
+        st.h2d.wait_event(st.free[slot])          # the call that used this slot two calls ago has drained
+        cols = H * D
+        flat = lambda t: t.view(B * S, cols)
+        h0 = 0
+        for g in host_head_groups(H):
+            h1 = h0 + g
+            for dst, src in ((dq, query), (dk, key), (dv, value)):
+                _native.copy2d_async(flat(dst), flat(src), h0 * D, g * D, st.h2d)
+            ev_in = torch.cuda.Event()
+            ev_in.record(st.h2d)
+            main.wait_event(ev_in)
+            for b in range(B):                    # list slices of one batch row and a head range are contiguous
+                sl = (slice(b, b + 1), slice(h0, h1))
+                _, lse_g, *_ = _flash_attn_forward(
+                    dq[b:b + 1, :, h0:h1], dk[b:b + 1, :, h0:h1], dv[b:b + 1, :, h0:h1], None, None, None,
+                    do[b:b + 1, :, h0:h1], None, None, None, None, None, None, None, None, None, None,
+                    None, None, None, None, None, None, softmax_scale, causal=False,
+                    attn_read_list=None if read_list is None else read_list[sl],
+                    attn_must_do_list=None if md is None else md[sl],
+                    attn_write_list=None if write_list is None else write_list[sl], thr=self.threshold)
+                if lse is not None:
+                    lse[b:b + 1, h0:h1].copy_(lse_g)
+            ev_out = torch.cuda.Event()
+            ev_out.record(main)
+            st.d2h.wait_event(ev_out)
+            _native.copy2d_async(flat(out), flat(do), h0 * D, g * D, st.d2h)
+            h0 = h1
+        st.free[slot].record(st.d2h)
+        self._host_done = st.free[slot]
+        if self._compact and write_list is not None:
+            _native.list_pack(write_list, self._bits[:B])
+        return (out, lse) if return_softmax_lse else out
+
+    def join_host_copies(self):
+        """Make the current stream wait for the downloads of the last host-resident call (stream-ordered)."""
+        ev = getattr(self, "_host_done", None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
+    def wait_host_copies(self):
+        """Block until the result of the last host-resident call is in host memory."""
+        ev = getattr(self, "_host_done", None)
+        if ev is not None:
+            ev.synchronize()
 
     @property
     def read_list(self) -> Optional[torch.Tensor]:
@@ -406,9 +550,11 @@ class SeqParallelLiteAttention:
     """`num_nodes` independent LiteAttention states, one per K/V shard (`split_idx`), for callers that shard the
     sequence and merge partial results by LSE (hopper/lite_attention.py:322-345; merge: flash_attn_combine)."""
 
-    def __init__(self, num_nodes: int, enable_skipping: bool = True, threshold: float = -10.0, max_batch_size: int = 4):
+    def __init__(self, num_nodes: int, enable_skipping: bool = True, threshold: float = -10.0, max_batch_size: int = 4,
+                 *, compact_state: Optional[bool] = None):
         self.num_nodes = num_nodes
-        self.lite_attention = [LiteAttention(enable_skipping, threshold, max_batch_size) for _ in range(num_nodes)]
+        self.lite_attention = [LiteAttention(enable_skipping, threshold, max_batch_size, compact_state=compact_state)
+                               for _ in range(num_nodes)]
         self.set_threshold(threshold)
 
     def __call__(self, query, key, value, split_idx: int, scale: Optional[float] = None,

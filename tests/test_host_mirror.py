@@ -150,6 +150,8 @@ def test_seq_parallel(book):
     q = torch.zeros(1, 10, 1, 128, dtype=torch.bfloat16)
     with pytest.raises(AssertionError):
         sp(q, q, q, split_idx=3)
+    sp = SeqParallelLiteAttention(2, compact_state=True)                # keyword-only extension reaches every split
+    assert all(x._compact for x in sp.lite_attention)
 
 
 def test_functional_api_has_no_cpu_fallback():

@@ -8,6 +8,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--seq", type=int, default=75600)
 ap.add_argument("--heads", type=int, default=40)
 ap.add_argument("--sparsity", type=float, default=0.42)
+ap.add_argument("--update", action="store_true", help="also run the list update kernel three times (thr = -1)")
 a = ap.parse_args()
 B, S, H, D = 1, a.seq, a.heads, 128
 g = torch.Generator(device="cuda").manual_seed(1000)
@@ -18,4 +19,8 @@ rl = (synth.exact_sparsity_list(B, H, qt, kt, a.sparsity, seed=1234, device="cud
 out = torch.empty_like(q); lse = torch.empty(B, H, S, device="cuda"); stat = torch.empty(B, H, qt, kt, device="cuda")
 for _ in range(3):
     N.fwd(q, k, v, out, lse, D ** -0.5, rl, stat)
+if a.update:
+    wl = torch.zeros_like(rl)
+    for _ in range(3):
+        N.skip_update(rl, None, wl, stat, B, H, qt, kt, -1.0)
 torch.cuda.synchronize()

@@ -420,7 +420,7 @@ def main():
         copy_floor_ms = max(3 * q.numel() * 2 * world / (float(bw[0]) * 1e9), q.numel() * 2 * world / (float(bw[1]) * 1e9)) * 1e3
         e2e = {"value": dense_flops * world / (e2e_ms * 1e-3) / 1e12, "unit": UNIT, "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": 3 * q.numel() * 2 * world, "d2h_bytes_per_step": q.numel() * 2 * world,
-               "api": "LiteAttention.__call__(pinned host q, k, v) -> pinned host O; uploads / forward + list update / downloads pipelined by head groups " + str(host_head_groups(H)) + " inside the call, two staging slots across calls",
+               "api": "LiteAttention.__call__(pinned host q, k, v) -> pinned host O; uploads / forward + list update / downloads pipelined by head groups inside the call (" + str(host_head_groups(H)) + " from idle, " + str(host_head_groups(H, True)) + " while the previous call is in flight), two staging slots across calls",
                "host_link": {"aggregate_h2d_gbs": float(bw[0]), "aggregate_d2h_gbs": float(bw[1]),
                              "copy_only_floor_ms_per_step": copy_floor_ms, "numa_node": numa_note,
                              "limiter": ("host<->device copies (PCIe / host memory), all ranks through one host"

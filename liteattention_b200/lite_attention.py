@@ -59,6 +59,7 @@ class _HostStage:
         self.h2d = torch.cuda.Stream(device)
         self.d2h = torch.cuda.Stream(device)
         self.calls = 0
+        self.last = None                                           # completion event of the most recent call
 
 
 _HOST_STAGES = {}
@@ -74,10 +75,12 @@ def _host_stage(device, shape, dtype):
     return st
 
 
-def host_head_groups(heads: int):
+def host_head_groups(heads: int, busy: bool = False):
     """Head-group sizes for streamed host calls: small first and last groups (the first upload and the last download
     are the only copies nothing overlaps), growing by 2x in between so that a group's upload always finishes under
-    the previous group's compute.  LITE_ATTENTION_HOST_CHUNKS="2,4,8,..." overrides (must sum to `heads`)."""
+    the previous group's compute.  `busy`: the previous host call is still in flight -- its compute already covers
+    this call's uploads, so one big group + the small last one (for a short drain) is enough and saves launches.
+    LITE_ATTENTION_HOST_CHUNKS="2,4,8,..." overrides (must sum to `heads`)."""
     env = os.getenv("LITE_ATTENTION_HOST_CHUNKS", "")
     if env:
         sizes = [int(x) for x in env.split(",")]
@@ -87,6 +90,8 @@ def host_head_groups(heads: int):
     if heads <= 3:
         return [heads]
     last = max(1, heads // 10)
+    if busy:
+        return [heads - last, last]
     sizes, left, nxt = [], heads - last, max(1, heads // 20)
     while left > 0:
         g = min(nxt, left, max(1, heads // 3))
@@ -444,8 +449,9 @@ class LiteAttention:
         st.h2d.wait_event(st.free[slot])          # the call that used this slot two calls ago has drained
         cols = H * D
         flat = lambda t: t.view(B * S, cols)
+        busy = st.last is not None and not st.last.query()     # some layer object's host call is still in flight
         h0 = 0
-        for g in host_head_groups(H):
+        for g in host_head_groups(H, busy):
             h1 = h0 + g
             for dst, src in ((dq, query), (dk, key), (dv, value)):
                 _native.copy2d_async(flat(dst), flat(src), h0 * D, g * D, st.h2d)
@@ -469,7 +475,7 @@ class LiteAttention:
             _native.copy2d_async(flat(out), flat(do), h0 * D, g * D, st.d2h)
             h0 = h1
         st.free[slot].record(st.d2h)
-        self._host_done = st.free[slot]
+        self._host_done = st.last = st.free[slot]
         if self._compact and write_list is not None:
             _native.list_pack(write_list, self._bits[:B])
         return (out, lse) if return_softmax_lse else out

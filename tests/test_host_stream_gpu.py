@@ -38,6 +38,28 @@ def test_host_call_equals_device_call(native_lib, b, s, h, compact):
     assert la_d.last_sparsity(b) == la_h.last_sparsity(b)
 
 
+def test_back_to_back_host_calls_without_waiting(native_lib):
+    """Calls queued while the previous one is still in flight take the coarse head-group schedule and the other staging
+    slot; results and lists must not change."""
+    b, s, h = 1, 6000, 40
+    q, k, v = _qkv(b, s, h, seed=21)
+    hq, hk, hv = (t.pin_memory() for t in (q, k, v))
+    dq, dk, dv = (t.to(DEV) for t in (q, k, v))
+    la_d = LiteAttention(True, -4.0, max_batch_size=b)
+    la_h = LiteAttention(True, -4.0, max_batch_size=b)
+    outs = [torch.empty_like(q).pin_memory() for _ in range(5)]
+    refs = []
+    for i in range(5):
+        refs.append(la_d(dq, dk, dv))
+        la_h(hq, hk, hv, out=outs[i])                                  # no wait in between
+    la_h.wait_host_copies()
+    torch.cuda.synchronize()
+    for i in range(5):
+        assert torch.equal(outs[i], refs[i].cpu()), f"call {i}"
+    ln = int(la_d.read_list[:b, ..., 0].max())
+    assert torch.equal(la_d.read_list[:b, ..., :ln + 1], la_h.read_list[:b, ..., :ln + 1])
+
+
 def test_host_call_with_must_do_and_user_out(native_lib):
     b, s, h = 1, 1300, 6
     q, k, v = _qkv(b, s, h, seed=7)
@@ -80,5 +102,7 @@ def test_head_group_schedule():
     for heads in (1, 2, 3, 4, 5, 8, 12, 16, 24, 40, 64, 96):
         g = host_head_groups(heads)
         assert sum(g) == heads and min(g) >= 1
+        gb = host_head_groups(heads, busy=True)
+        assert sum(gb) == heads and min(gb) >= 1 and len(gb) <= 2
         if heads >= 20:
             assert g[0] <= heads // 10 and g[-1] <= heads // 8          # small first upload, small last download

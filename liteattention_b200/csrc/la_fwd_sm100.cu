@@ -27,7 +27,7 @@
 //         units); the exponentials never wait for the tile's own max and O is almost never rescaled.  The QK-skip
 //         statistic is always computed from the true running max.
 //       - the verdict (does any row max run ahead of m_ref by more than 8?) needs the full-row max: the two warps
-//         that own a row exchange half-row maxima through smem and a pair of split named barriers.  If it fails,
+//         that own a row exchange half-row maxima through smem and one named barrier.  If it fails,
 //         the tile is redone exactly, out of line (softmax_slow_tile): m_ref := true max, l and O rescaled.
 //       - 2 of every 8 column pairs (staggered between the two column halves) take their exp2 on the FMA pipe (Cody-Waite + cubic), which balances the MUFU
 //         pipe against instruction dispatch; S(i+1) is pulled from TMEM while P(i) is being published; the
@@ -84,7 +84,7 @@ constexpr uint32_t kOffK = kOffQ + kQBytes;
 constexpr uint32_t kOffV = kOffK + 2 * kKVBytes;
 constexpr uint32_t kOffBar = kOffV + 2 * kKVBytes;
 constexpr uint32_t kOffXchg = kOffBar + 256;
-constexpr uint32_t kOffLx = kOffXchg + 2 * kSoftmaxThreads * 4;
+constexpr uint32_t kOffLx = kOffXchg + 2 * kSoftmaxThreads * 8;   // {tile tag, half-row max} per thread and S buffer
 constexpr uint32_t kOffStat = kOffLx + kSoftmaxThreads * 4;
 constexpr uint32_t kOffSeq = kOffStat + kFwdMaxTiles * 4;
 constexpr uint32_t kSmemUsed = kOffSeq + kFwdMaxTiles * 2;
@@ -556,8 +556,8 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       a.s_addr = s_tmem(i);
       a.p_addr = tmem_base + kTmemS + buf * kN + wg * (kHalfN / 2) + lane_field;
       a.o_addr = tmem_base + kTmemO + wg * 64 + lane_field;
-      a.xchg_mine = xchg_base + (buf * kSoftmaxThreads + tid) * 4;
-      a.xchg_other = xchg_base + (buf * kSoftmaxThreads + (tid ^ 128)) * 4;
+      a.xchg_mine = xchg_base + (buf * kSoftmaxThreads + tid) * 8 + 4;
+      a.xchg_other = xchg_base + (buf * kSoftmaxThreads + (tid ^ 128)) * 8 + 4;
       a.bar_id = pair_bar;
       // PV(i-1) retiring is what frees V stage (i-1)&1: phase ((i-1)>>1) of that stage's empty barrier.  When tile i
       // is being processed PV(i-2) has retired (S(i) was committed after it) and PV(i+1) cannot have been issued, so
@@ -585,6 +585,9 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       if (lane == 0) mbar_arrive(bar(kBarPFull + (i & 1)));
     };
 
+    // Exchange slots are {tile tag, value}; no hot-loop tile has tag 0xffffffff.
+    sts_u32(xchg_base + tid * 8, 0xffffffffu);
+    sts_u32(xchg_base + (kSoftmaxThreads + tid) * 8, 0xffffffffu);
     LA_PROF_DECL(7);
 #ifdef LA_PROFILE_CLOCKS
     long long prof_t_s0 = 0, prof_t_first = 0, prof_t_loop_end = 0;
@@ -610,8 +613,8 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       const int buf = i & 1;
       // P (bf16 pairs) goes over the first 88 columns of this S buffer: wg0 -> [0,44), wg1 -> [44,88).
       const uint32_t p_addr = tmem_base + kTmemS + buf * kN + wg * (kHalfN / 2) + lane_field;
-      const uint32_t xchg_mine = xchg_base + (buf * kSoftmaxThreads + tid) * 4;
-      const uint32_t xchg_other = xchg_base + (buf * kSoftmaxThreads + (tid ^ 128)) * 4;
+      const uint32_t xchg_mine = xchg_base + (buf * kSoftmaxThreads + tid) * 8;
+      const uint32_t xchg_other = xchg_base + (buf * kSoftmaxThreads + (tid ^ 128)) * 8;
       const uint32_t next_bar = bar(kBarSFull + (buf ^ 1));
       const uint32_t next_par = ((i + 1) >> 1) & 1;
       const bool more = i + 1 < T;
@@ -632,8 +635,11 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       uint64_t acc0 = pack2(0.f, 0.f), acc1 = pack2(0.f, 0.f);
       float mx0 = -INFINITY, mx1 = -INFINITY;
       constexpr int kQuads = kHalfN / 4;   // 22 groups of 4 columns
+#ifndef LA_XCHG_FLAG
+#define LA_XCHG_FLAG 0                     // 1: half-row max exchange through tagged smem slots (round-2 experiment), 0: named barrier
+#endif
 #ifndef LA_POST_Q
-#define LA_POST_Q 22                       // quad index at which the half-row max is posted (22 = after the loop)
+#define LA_POST_Q (LA_XCHG_FLAG ? 18 : 22) // quad index at which the half-row max is posted (22 = after the loop)
 #endif
       constexpr int kPostQ = LA_POST_Q;
 #ifndef LA_STAT_Q
@@ -644,10 +650,14 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 #endif
       float m_half = 0.f, m_loc = 0.f;
       bool ready = false;
-      // Tuning knobs kept from the same-box sweeps (tools/build_variants.py + tools/sustained.py): posting the half-row
-      // max before the last quads (LA_POST_Q < 22: the max of the remaining quads is taken ahead of their exponentials
-      // so that the exchange runs under them), where the statistic is reduced, and whether the MUFU statements are
-      // pinned in program order, all measured within +-1 % of each other; the defaults are the best of that sweep.
+      // Half-row max exchange between the two warps that own the same 32 rows: a full-rendezvous named barrier after the
+      // loop (default), or -- LA_XCHG_FLAG, a round-2 experiment kept as a knob -- tagged smem slots: the max of the
+      // remaining quads is taken ahead of their exponentials and posted at quad LA_POST_Q as {tile index, value}, the
+      // partner's slot is polled after the loop; no barrier, and unlike round 1's split arrive/sync barrier it cannot
+      // slip a phase (a tag matches exactly one tile).  It is 1.2-1.5 % faster in short bursts (tools/ab.py) and
+      // 0.4 % slower inside bench.py's power-capped steady state, where the busier pipes only lower the clock
+      // (profiles/ab_r2.txt, calls 28-31); the barrier stays.  Where the statistic is reduced and whether the MUFU
+      // statements are pinned in program order measured within +-1 % of each other.
       auto post_and_fetch = [&](int q_from) {
 #pragma unroll
         for (int qq = q_from; qq < kQuads; ++qq) {
@@ -655,13 +665,38 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           mx1 = fmax3(mx1, s[4 * qq + 2], s[4 * qq + 3]);
         }
         m_half = fmaxf(mx0, mx1);
-        sts_f32(xchg_mine, m_half);
+#if LA_XCHG_FLAG
+        // Tagged post: {tile index, half-row max} in one 8-byte store.  The partner polls for the tag after its own loop
+        // (consume_max below), so nothing blocks here and the exchange latency runs under the remaining exponentials.
+        sts_v2_u32(xchg_mine, (uint32_t)i, __float_as_uint(m_half));
+        ready = more && mbar_test_wait(next_bar, next_par);
+#else
+        sts_f32(xchg_mine + 4, m_half);
         // Is S(i+1) there yet?  (Asked here so that the answer's latency runs under the verdict.)
         ready = more && mbar_try_wait(next_bar, next_par);
         // Exchange the half-row maxima between the two warps that own the same 32 rows.  Passing the barrier also
         // means the partner has all of its S columns in registers, the condition for our P to land on them.
         named_bar_sync(pair_bar, 64);
-        m_loc = fmaxf(m_half, lds_f32(xchg_other));
+        m_loc = fmaxf(m_half, lds_f32(xchg_other + 4));
+#endif
+      };
+      auto consume_max = [&]() {
+#if LA_XCHG_FLAG
+        // Seeing the partner's tag for this tile also means it has all of its S columns in registers (it posts after
+        // its wait::ld), the condition for our P to land on them.  Two slots (one per S buffer) are enough: the
+        // partner cannot post tile i+2 before it has seen our post of tile i+1, which follows this read.
+        uint32_t tag, val, spins = 0;
+        do {
+          lds_v2_u32_volatile(xchg_other, tag, val);
+          if (++spins > LA_WATCHDOG_SPINS) __trap();      // a protocol bug must not hang the box (see la_ptx.cuh)
+        } while (tag != (uint32_t)i);
+        m_loc = fmaxf(m_half, __uint_as_float(val));
+        // The poll loop exits lane by lane: reconverge before anything .sync.aligned depends on a per-lane answer
+        // (`ready` gates the warp-wide tcgen05.ld of S(i+1)).
+        __syncwarp();
+        if (more && !ready) ready = mbar_test_wait(next_bar, next_par);
+        ready = __all_sync(0xffffffffu, ready);
+#endif
       };
       // The two warps that share a sub-partition run this loop in near lock-step; each column half has its own mask so
       // that their FMA-pipe pairs do not coincide.
@@ -706,6 +741,7 @@ la_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       if (kPolyMaskB == kPolyMask || wg == 0) exp_loop(std::integral_constant<uint32_t, kPolyMask>{});
       else exp_loop(std::integral_constant<uint32_t, kPolyMaskB>{});
       if (kPostQ >= kQuads) post_and_fetch(kQuads);
+      consume_max();
       LA_CLK(t2);
       LA_ACC(1, t1, t2);
       // Both warps of the pair see the same m_loc and m_ref for the same rows => the same verdict.

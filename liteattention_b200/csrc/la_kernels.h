@@ -9,7 +9,7 @@ namespace la {
 
 constexpr int kFwdThreads = 384;        // 8 softmax warps + one warpgroup holding the TMA warp and the MMA warp
 constexpr int kFwdMaxTiles = 2048;      // K tiles one CTA can visit (seqlen_k <= 360448)
-constexpr int kFwdSmemBytes = 229632;   // dynamic shared memory of la_fwd_kernel (incl. 1 KB alignment slack)
+constexpr int kFwdSmemBytes = 231680;   // dynamic shared memory of la_fwd_kernel (incl. 1 KB alignment slack)
 
 struct FwdKernelArgs {
   __nv_bfloat16* out;

@@ -276,6 +276,14 @@ int la_fwd_skip_sm100(const la_fwd_params* fwd, const la_update_params* upd, voi
   LA_CHECK_ARG(fwd != nullptr && upd != nullptr, "la_fwd_skip_sm100: params are NULL");
   LA_CHECK_ARG(fwd->read_list != nullptr && fwd->tile_stat != nullptr,
                "la_fwd_skip_sm100: the forward needs read_list and tile_stat to feed the update");
+  // The update walks the rows the forward just produced: its geometry must be the forward's (a mismatch would read
+  // and write the lists and the statistic out of bounds).
+  {
+    const int qt = (fwd->seqlen_q + 127) / 128, kt = (fwd->seqlen_k + 175) / 176;
+    LA_CHECK_ARG(upd->b == fwd->b && upd->h == fwd->h && upd->qtiles == qt && upd->ktiles == kt,
+                 "la_fwd_skip_sm100: update geometry (b %d, h %d, qtiles %d, ktiles %d) does not match the forward's "
+                 "(b %d, h %d, qtiles %d, ktiles %d)", upd->b, upd->h, upd->qtiles, upd->ktiles, fwd->b, fwd->h, qt, kt);
+  }
   int rc = la_fwd_sm100(fwd, stream);
   if (rc) return rc;
   la_update_params u = *upd;

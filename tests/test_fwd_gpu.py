@@ -305,6 +305,32 @@ def test_error_paths(native_lib):
         flash_attn_func(qg, q, q).float().sum().backward()
 
 
+def test_c_abi_rejects_update_geometry_that_is_not_the_forwards(native_lib):
+    """la_fwd_skip_sm100 cross-checks the update's (b, h, qtiles, ktiles) against the forward's: a mismatch would walk the
+    lists and the statistic out of bounds."""
+    import ctypes
+    N = native_lib
+    b, s, h = 1, 700, 2
+    q = torch.zeros(b, s, h, 128, dtype=torch.bfloat16, device=DEV)
+    qt, kt = H.tiles(s)
+    rl = torch.zeros(b, h, qt, kt + 1, dtype=torch.int32, device=DEV)
+    rl[..., 0], rl[..., 1] = 2, kt - 1
+    wl = torch.zeros_like(rl)
+    stat = torch.empty(b, h, qt, kt, device=DEV)
+    out, lse = torch.empty_like(q), torch.empty(b, h, s, device=DEV)
+    p = N.make_fwd_params(q, q, q, out, lse, 128 ** -0.5, rl, stat)
+    for bad in ({"ktiles": kt + 1}, {"qtiles": qt + 1}, {"h": h + 1}, {"b": b + 1}):
+        geo = dict(b=b, h=h, qtiles=qt, ktiles=kt)
+        geo.update(bad)
+        u = N.make_update_params(rl, None, wl, stat, geo["b"], geo["h"], geo["qtiles"], geo["ktiles"], -3.0)
+        rc = N.lib().la_fwd_skip_sm100(ctypes.byref(p), ctypes.byref(u), None)
+        assert rc != 0 and b"geometry" in N.lib().la_last_error()
+    u = N.make_update_params(rl, None, wl, stat, b, h, qt, kt, -3.0)
+    with torch.cuda.device(q.device):
+        assert N.lib().la_fwd_skip_sm100(ctypes.byref(p), ctypes.byref(u), N._stream(q.device)) == 0
+    torch.cuda.synchronize()
+
+
 def test_empty_and_clamped_lists(native_lib):
     """len = 0 row -> zeros / -inf (documented divergence: the reference still walks range [row[1], row[2]]);
     out-of-range tile indices are clamped instead of read out of bounds."""

@@ -177,3 +177,26 @@ def test_c_abi_exports_every_declared_symbol(native_lib):
     assert ctypes.sizeof(native_lib.FwdParams) == 5 * 8 + 12 * 8 + 6 * 4 + 4 + 4 + 2 * 8 + 4 * 4 + 8 * 8   # + out_is_f32, n_out_peers, out_rows_per_peer, reserved, out_peer[8]
     assert ctypes.sizeof(native_lib.RopeParams) == 4 * 8 + 3 * 8 + 6 * 4
     assert ctypes.sizeof(native_lib.UpdateParams) == 4 * 8 + 4 * 4 + 4 + 4 + 8
+
+
+def test_host_head_group_schedule():
+    """Head groups of the host-resident call (liteattention_b200/lite_attention.py:host_head_groups): a partition of the
+    heads with a small first upload and a small last download; one big group + the small last one while another call is
+    in flight; LITE_ATTENTION_HOST_CHUNKS overrides and is validated."""
+    from liteattention_b200.lite_attention import host_head_groups
+    for heads in (1, 2, 3, 4, 5, 8, 12, 16, 24, 40, 64, 96):
+        g = host_head_groups(heads)
+        assert sum(g) == heads and min(g) >= 1
+        gb = host_head_groups(heads, busy=True)
+        assert sum(gb) == heads and min(gb) >= 1 and len(gb) <= 2
+        if heads >= 20:
+            assert g[0] <= heads // 10 and g[-1] <= heads // 8
+    assert host_head_groups(40) == [2, 4, 8, 13, 9, 4] and host_head_groups(40, True) == [36, 4]
+    import os
+    os.environ["LITE_ATTENTION_HOST_CHUNKS"] = "10,10,20"
+    try:
+        assert host_head_groups(40) == [10, 10, 20]
+        with pytest.raises(ValueError):
+            host_head_groups(32)
+    finally:
+        del os.environ["LITE_ATTENTION_HOST_CHUNKS"]

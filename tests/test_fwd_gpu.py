@@ -331,6 +331,48 @@ def test_c_abi_rejects_update_geometry_that_is_not_the_forwards(native_lib):
     torch.cuda.synchronize()
 
 
+def test_maximum_number_of_k_tiles(native_lib):
+    """The largest K extent the kernels accept: 2048 list tiles (seqlen_k = 360 398, ragged last tile), dense and
+    list-gated with the update on top (64 bitmap words per row = two lane groups in the update kernel); one more tile is
+    refused with an error instead of overrunning the tile sequence in shared memory."""
+    from liteattention_b200 import flash_attn_func
+    kt, thr = 2048, -6.0
+    sk, sq, h = kt * 176 - 50, 200, 1
+    g = torch.Generator(device=DEV).manual_seed(5)
+    q = (torch.randn(1, sq, h, 128, device=DEV, generator=g) * 2).to(torch.bfloat16)
+    k, v = (torch.randn(1, sk, h, 128, device=DEV, generator=g).to(torch.bfloat16) for _ in range(2))
+    out, lse = flash_attn_func(q, k, v, return_softmax_lse=True)
+    o_ref, lse_ref = _masked_ref(q, k, v)
+    _assert_close(out, lse, o_ref, lse_ref)
+
+    qt = 2
+    rng = np.random.default_rng(3)
+    keep = np.repeat(rng.random((1, h, qt, kt // 4)) < 0.5, 4, axis=-1)
+    keep[..., kt - 1] = True
+    rl = torch.zeros(1, h, qt, kt + 1, dtype=torch.int32)
+    for m in range(qt):
+        row = sl.encode_keep_mask(keep[0, 0, m].tolist())
+        rl[0, 0, m, :len(row)] = torch.tensor(row, dtype=torch.int32)
+    rl = rl.to(DEV)
+    wl = torch.full_like(rl, -7)
+    stat = torch.full((1, h, qt, kt), float("nan"), device=DEV)
+    out2, lse2 = torch.empty_like(out), torch.empty_like(lse)
+    native_lib.fwd_skip(q, k, v, out2, lse2, 128 ** -0.5, rl, None, wl, stat, thr)
+    torch.cuda.synchronize()
+    keep_t = torch.from_numpy(keep).to(DEV)
+    o_ref2, lse_ref2 = _masked_ref(q, k, v, keep_t)
+    _assert_close(out2, lse2, o_ref2, lse_ref2)
+    st = stat.cpu()
+    assert torch.equal(~torch.isnan(st), keep_t.cpu()), "visited tiles are not the listed ones"
+    exp, _ = H.c_oracle_step(rl.cpu().view(-1, kt + 1).numpy(), None, np.nan_to_num(st.view(-1, kt).numpy(), nan=0.0), thr)
+    assert H.rows_equal_upto_len(wl.cpu().view(-1, kt + 1).numpy(), exp)
+    assert 0 < int(wl[..., 0].min()) and int(wl[..., 0].max()) <= kt
+
+    kk = torch.zeros(1, sk + 200, h, 128, dtype=torch.bfloat16, device=DEV)          # 2049 tiles
+    with pytest.raises(RuntimeError):
+        flash_attn_func(q, kk, kk)
+
+
 def test_empty_and_clamped_lists(native_lib):
     """len = 0 row -> zeros / -inf (documented divergence: the reference still walks range [row[1], row[2]]);
     out-of-range tile indices are clamped instead of read out of bounds."""

@@ -54,10 +54,10 @@ def _run_kernel(native_lib, read, md, stat, thr, b=1, h=1):
     return wl.cpu().numpy(), int(ovf.item())
 
 
-@pytest.mark.parametrize("kt", [2, 7, 33, 187, 430])
+@pytest.mark.parametrize("kt", [2, 7, 33, 187, 430, 1024, 1025, 2048])       # 1025 / 2048: more than one 32-word group
 @pytest.mark.parametrize("with_md", [False, True])
 def test_update_kernel_bit_exact_vs_c_oracle(native_lib, kt, with_md):
-    rows = 3000 if kt < 100 else 1200
+    rows = 3000 if kt < 100 else 1200 if kt < 1000 else 250
     read, md, stat = _random_case(rows, kt, seed=kt * 2 + with_md, with_md=with_md)
     for thr in (-1.0, 0.0, float("inf"), float("-inf")):
         got, n_ovf = _run_kernel(native_lib, read, md if with_md else None, stat, thr)

@@ -70,6 +70,12 @@ def _host_stage(device, shape, dtype):
     st = _HOST_STAGES.get(key)
     if st is None:
         if len(_HOST_STAGES) >= 2:
+            # The staging buffers are used by copies on side streams the caching allocator knows nothing about: drain
+            # everything before their memory can be handed out again.
+            for old in _HOST_STAGES.values():
+                old.h2d.synchronize()
+                old.d2h.synchronize()
+            torch.cuda.synchronize(device)
             _HOST_STAGES.clear()
         st = _HOST_STAGES[key] = _HostStage(device, shape, dtype)
     return st

@@ -60,6 +60,23 @@ def test_back_to_back_host_calls_without_waiting(native_lib):
     assert torch.equal(la_d.read_list[:b, ..., :ln + 1], la_h.read_list[:b, ..., :ln + 1])
 
 
+def test_staging_sets_are_recycled_safely(native_lib):
+    """Only two staging sets (one per tensor shape) are kept; a third shape drains and drops them while earlier calls may
+    still be in flight.  Results must not be disturbed."""
+    las, outs, refs = [], [], []
+    for i, s in enumerate((1100, 1900, 2700, 1100)):
+        q, k, v = _qkv(1, s, 4, seed=40 + i)
+        la = LiteAttention(enable_skipping=False)
+        outs.append(la(q.pin_memory(), k.pin_memory(), v.pin_memory(), out=torch.empty_like(q).pin_memory()))   # no wait
+        refs.append(LiteAttention(enable_skipping=False)(q.to(DEV), k.to(DEV), v.to(DEV)))
+        las.append(la)
+    for la in las:
+        la.wait_host_copies()
+    torch.cuda.synchronize()
+    for o, r in zip(outs, refs):
+        assert torch.equal(o, r.cpu())
+
+
 def test_host_call_with_must_do_and_user_out(native_lib):
     b, s, h = 1, 1300, 6
     q, k, v = _qkv(b, s, h, seed=7)
